@@ -1,0 +1,409 @@
+// Element-wise, gather, shift and axis-reduction kernels (HBM-bound family, SURVEY 8a rows a3-a6,
+// a8, a13-a16, a18).  All arithmetic is plain IEEE double with explicit __dmul_rn/__dadd_rn where
+// the reference does a separate multiply and add, so these paths are bit-identical to the oracle.
+#include "kernels.cuh"
+
+namespace gtp {
+
+// ------------------------------------------------------------------------------------------
+// generic N-D element-wise kernel
+// ------------------------------------------------------------------------------------------
+template <int OP>
+__global__ void __launch_bounds__(256) k_ew(const EwParams p) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 lin = (u64)blockIdx.x * blockDim.x + threadIdx.x; lin < p.total; lin += stride) {
+    u64 rem = lin;
+    long long ao = p.a_base, bo = p.b_base, oo = p.o_base;
+    bool a_ok = true, b_ok = true;
+    unsigned fidx = 0;
+    bool first = (lin == 0);
+#pragma unroll 1
+    for (int d = p.ndim - 1; d >= 0; --d) {
+      unsigned e = p.ext[d];
+      unsigned i = (unsigned)(rem % e);
+      rem /= e;
+      ao += (long long)i * p.a_str[d];
+      bo += (long long)i * p.b_str[d];
+      oo += (long long)i * p.o_str[d];
+      a_ok &= i < p.a_ext[d];
+      b_ok &= i < p.b_ext[d];
+      if (d == p.fax) fidx = i;
+    }
+    double r;
+    if (OP == EW_COPY) {
+      double a = p.a[ao];
+      r = p.fac ? __dmul_rn(a, p.fac[fidx]) : a;
+    } else if (OP == EW_ADD || OP == EW_SUB) {
+      r = 0.0;
+      if (a_ok) r = __dadd_rn(r, p.a[ao]);
+      if (b_ok) r = (OP == EW_ADD) ? __dadd_rn(r, p.b[bo]) : __dsub_rn(r, p.b[bo]);
+    } else if (OP == EW_MASK) {
+      r = p.keep[fidx] ? p.a[ao] : 0.0;
+    } else if (OP == EW_SCALE_DEV) {
+      r = __dmul_rn(*p.s, p.a[ao]);
+    } else if (OP == EW_DIV_DEV) {
+      r = __ddiv_rn(p.a[ao], *p.s);
+    } else if (OP == EW_NEG) {
+      r = -p.a[ao];
+    } else if (OP == EW_ADD_FIRST) {
+      r = first ? __dadd_rn(p.a[ao], *p.s) : p.a[ao];
+    } else if (OP == EW_SUB_FIRST) {
+      r = first ? __dsub_rn(p.a[ao], *p.s) : p.a[ao];
+    } else {  // EW_RSUB_FIRST
+      r = -(first ? __dsub_rn(p.a[ao], *p.s) : p.a[ao]);
+    }
+    p.out[oo] = r;
+  }
+}
+
+static Shape strides_of(const Shape& shape) {
+  Shape st(shape.size(), 1);
+  for (int i = (int)shape.size() - 2; i >= 0; --i) st[i] = st[i + 1] * shape[i + 1];
+  return st;
+}
+
+void launch_ew(Ctx& ctx, EwOp op, const Shape& box, const EwOperand& a, const EwOperand* b, double* out,
+               const Shape& out_shape, const Shape& out_lo, int fax, const double* fac,
+               const unsigned char* keep, const double* s) {
+  const int nd = (int)box.size();
+  GTP_CHECK(nd <= MAXD, GTP_ERR_ARG, "ndim exceeds GTP_MAX_NDIM");
+  u64 total = prod(box);
+  if (total == 0) return;
+  // per-axis description
+  struct Ax {
+    u64 ext, a_ext, b_ext;
+    long long a_str, b_str, o_str;
+    bool special;
+  };
+  std::vector<Ax> ax(nd);
+  Shape ast = strides_of(a.shape), ost = strides_of(out_shape), bst;
+  if (b) bst = strides_of(b->shape);
+  long long a_base = 0, b_base = 0, o_base = 0;
+  for (int d = 0; d < nd; d++) {
+    ax[d].ext = box[d];
+    ax[d].a_ext = a.valid.empty() ? box[d] : std::min<u64>(a.valid[d], box[d]);
+    ax[d].b_ext = (b && !b->valid.empty()) ? std::min<u64>(b->valid[d], box[d]) : box[d];
+    ax[d].a_str = (long long)ast[d];
+    ax[d].b_str = b ? (long long)bst[d] : 0;
+    ax[d].o_str = (long long)ost[d];
+    ax[d].special = (d == fax);
+    a_base += (long long)(a.lo.empty() ? 0 : a.lo[d]) * (long long)ast[d];
+    if (b) b_base += (long long)(b->lo.empty() ? 0 : b->lo[d]) * (long long)bst[d];
+    o_base += (long long)(out_lo.empty() ? 0 : out_lo[d]) * (long long)ost[d];
+  }
+  // drop unit axes, then merge axis d+1 into d when the pair is contiguous in every tensor and
+  // fully valid (so validity / factor indexing is unaffected)
+  std::vector<Ax> c;
+  for (int d = 0; d < nd; d++)
+    if (ax[d].ext != 1 || ax[d].special) c.push_back(ax[d]);
+  if (c.empty()) c.push_back(Ax{1, 1, 1, 0, 0, 0, false});
+  for (size_t d = c.size(); d-- > 1;) {
+    Ax& hi = c[d - 1];
+    Ax& lo = c[d];
+    bool full = lo.a_ext == lo.ext && lo.b_ext == lo.ext && hi.a_ext == hi.ext && hi.b_ext == hi.ext;
+    bool contig = hi.a_str == lo.a_str * (long long)lo.ext && hi.o_str == lo.o_str * (long long)lo.ext &&
+                  (!b || hi.b_str == lo.b_str * (long long)lo.ext);
+    if (full && contig && !hi.special && !lo.special && hi.ext * lo.ext < (1ull << 31)) {
+      hi.ext *= lo.ext;
+      hi.a_ext = hi.b_ext = hi.ext;
+      hi.a_str = lo.a_str;
+      hi.b_str = lo.b_str;
+      hi.o_str = lo.o_str;
+      c.erase(c.begin() + d);
+    }
+  }
+  EwParams p;
+  memset(&p, 0, sizeof(p));
+  p.ndim = (int)c.size();
+  p.fax = -1;
+  p.total = total;
+  for (int d = 0; d < p.ndim; d++) {
+    GTP_CHECK(c[d].ext < (1ull << 32), GTP_ERR_ARG, "axis too long");
+    p.ext[d] = (unsigned)c[d].ext;
+    p.a_ext[d] = (unsigned)c[d].a_ext;
+    p.b_ext[d] = b ? (unsigned)c[d].b_ext : 0;
+    p.a_str[d] = c[d].a_str;
+    p.b_str[d] = c[d].b_str;
+    p.o_str[d] = c[d].o_str;
+    if (c[d].special) p.fax = d;
+  }
+  p.a_base = a_base;
+  p.b_base = b_base;
+  p.o_base = o_base;
+  p.a = a.p;
+  p.b = b ? b->p : nullptr;
+  p.out = out;
+  p.fac = fac;
+  p.keep = keep;
+  p.s = s;
+  int block = 256;
+  u64 want = (total + block - 1) / block;
+  int grid = (int)std::min<u64>(want, (u64)ctx.sm_count * 16);
+  switch (op) {
+#define CASE(O) case O: GTP_LAUNCH(ctx, k_ew<O>, grid, block, 0, p); break;
+    CASE(EW_COPY) CASE(EW_ADD) CASE(EW_SUB) CASE(EW_MASK) CASE(EW_SCALE_DEV) CASE(EW_DIV_DEV)
+    CASE(EW_NEG) CASE(EW_ADD_FIRST) CASE(EW_SUB_FIRST) CASE(EW_RSUB_FIRST)
+#undef CASE
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void k_fill(double* dst, u64 n, double v) {
+  u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = v;
+}
+void launch_fill(Ctx& ctx, double* dst, u64 n, double value) {
+  if (n == 0) return;
+  if (value == 0.0 && !std::signbit(value)) {
+    GTP_CUDA(cudaMemsetAsync(dst, 0, n * sizeof(double), ctx.stream));
+    return;
+  }
+  int grid = (int)std::min<u64>((n + 255) / 256, (u64)ctx.sm_count * 16);
+  GTP_LAUNCH(ctx, k_fill, grid, 256, 0, dst, n, value);
+}
+
+// Sequential factor tables (one thread; <= a few thousand steps): the reference builds these
+// incrementally in exactly this order, so the table is bit-identical.
+__global__ void k_factors(int kind, u64 n, u64 len, const double* m, double* fac) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (kind == 0) {  // derivative :472-479
+    double ff = 1.0;
+    for (u64 i = 1; i <= n; i++) ff = __dmul_rn(ff, (double)(unsigned)i);
+    for (u64 k = 0; k < len; k++) {
+      fac[k] = ff;
+      ff = __dmul_rn(ff, __ddiv_rn((double)(unsigned)(n + k + 1), (double)(unsigned)(k + 1)));
+    }
+  } else if (kind == 1) {  // taylor_expansion_of_coeff :499-507
+    double f = 1.0;
+    fac[0] = 1.0;
+    for (u64 k = 1; k < len; k++) {
+      f = __dmul_rn(f, __ddiv_rn((double)(unsigned)(n + k), (double)(unsigned)k));
+      fac[k] = f;
+    }
+  } else {  // powers :557-565
+    double f = 1.0, mm = *m;
+    for (u64 k = 0; k < len; k++) {
+      fac[k] = f;
+      f = __dmul_rn(f, mm);
+    }
+  }
+}
+void launch_factors(Ctx& ctx, int kind, u64 n, u64 len, const double* m, double* fac) {
+  GTP_LAUNCH(ctx, k_factors, 1, 32, 0, kind, n, len, m, fac);
+}
+
+// ------------------------------------------------------------------------------------------
+// shift_down.  out[o,0,i] = in[o,n,i] + sum_{a<n} in[o,a,i]   (or the plain axis sum when
+// len <= n+1); out[o,a',i] = in[o,n+a',i].  Summation order follows ndarray 0.15.6 sum_axis:
+//  * inner > 1  (axis is not the minimum-stride axis): res = 0; res += in[a] for a ascending
+//  * inner == 1 (contiguous lanes): 8-way unrolled fold (numeric_util::unrolled_fold)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_shift_down_strided(const double* __restrict__ in, double* __restrict__ out,
+                                                           u64 outer, u64 len, u64 inner, u64 n, u64 out_len) {
+  // one thread per (o, i): the slices a = 0..len-1 are `inner` apart, so a warp reads 32
+  // consecutive doubles of each slice (coalesced), and copies the tail slices as it goes.
+  const u64 total = outer * inner;
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  const u64 head = (len <= n + 1) ? len : n;  // slices folded into the sum_axis part
+  for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    u64 o = t / inner, i = t - o * inner;
+    const double* src = in + o * len * inner + i;
+    double* dst = out + o * out_len * inner + i;
+    double acc = 0.0;
+    u64 a = 0;
+    for (; a + 4 <= head; a += 4) {  // 4 independent loads in flight
+      double v0 = src[(a + 0) * inner], v1 = src[(a + 1) * inner];
+      double v2 = src[(a + 2) * inner], v3 = src[(a + 3) * inner];
+      acc = __dadd_rn(acc, v0);
+      acc = __dadd_rn(acc, v1);
+      acc = __dadd_rn(acc, v2);
+      acc = __dadd_rn(acc, v3);
+    }
+    for (; a < head; a++) acc = __dadd_rn(acc, src[a * inner]);
+    if (len <= n + 1) {
+      dst[0] = acc;
+    } else {
+      dst[0] = __dadd_rn(src[n * inner], acc);
+      for (u64 k = 1; k < out_len; k++) dst[k * inner] = src[(n + k) * inner];
+    }
+  }
+}
+
+// contiguous lanes: 8 threads cooperate on one lane, thread l owning p_l of unrolled_fold
+__global__ void __launch_bounds__(256) k_shift_down_lanes(const double* __restrict__ in, double* __restrict__ out,
+                                                         u64 outer, u64 len, u64 n, u64 out_len) {
+  const u64 lanes_per_block = blockDim.x / 8;
+  const unsigned l = threadIdx.x & 7;
+  const unsigned full = 0xffffffffu;
+  const u64 head = (len <= n + 1) ? len : n;
+  for (u64 o = (u64)blockIdx.x * lanes_per_block + threadIdx.x / 8; o < (outer + lanes_per_block - 1) / lanes_per_block * lanes_per_block;
+       o += (u64)gridDim.x * lanes_per_block) {
+    bool active = o < outer;
+    const double* src = in + (active ? o : 0) * len;
+    double p = 0.0;
+    u64 chunks = head / 8;
+    if (active)
+      for (u64 c = 0; c < chunks; c++) p = __dadd_rn(p, src[c * 8 + l]);
+    // q_l = p_l + p_{l+4} for l < 4
+    double hi = __shfl_down_sync(full, p, 4, 8);
+    double q = __dadd_rn(p, hi);
+    double q1 = __shfl_sync(full, q, 1, 8), q2 = __shfl_sync(full, q, 2, 8), q3 = __shfl_sync(full, q, 3, 8);
+    if (active && l == 0) {
+      double acc = 0.0;
+      acc = __dadd_rn(acc, q);
+      acc = __dadd_rn(acc, q1);
+      acc = __dadd_rn(acc, q2);
+      acc = __dadd_rn(acc, q3);
+      for (u64 a = chunks * 8; a < head; a++) acc = __dadd_rn(acc, src[a]);
+      double* dst = out + o * out_len;
+      dst[0] = (len <= n + 1) ? acc : __dadd_rn(src[n], acc);
+    }
+    if (active && len > n + 1) {
+      double* dst = out + o * out_len;
+      for (u64 k = 1 + l; k < out_len; k += 8) dst[k] = src[n + k];
+    }
+  }
+}
+
+void launch_shift_down(Ctx& ctx, const double* in, double* out, u64 outer, u64 len, u64 inner, u64 n,
+                       bool last_axis) {
+  u64 out_len = (len <= n + 1) ? 1 : len - n;
+  if (inner > 1 || !last_axis) {
+    u64 total = outer * inner;
+    int grid = (int)std::max<u64>(1, std::min<u64>((total + 255) / 256, (u64)ctx.sm_count * 32));
+    GTP_LAUNCH(ctx, k_shift_down_strided, grid, 256, 0, in, out, outer, len, inner, n, out_len);
+  } else {
+    u64 lanes_per_block = 256 / 8;
+    int grid = (int)std::max<u64>(1, std::min<u64>((outer + lanes_per_block - 1) / lanes_per_block, (u64)ctx.sm_count * 32));
+    GTP_LAUNCH(ctx, k_shift_down_lanes, grid, 256, 0, in, out, outer, len, n, out_len);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_sum_partial(const double* __restrict__ in, u64 n, double* partial) {
+  __shared__ double sh[8];
+  double acc = 0.0;
+  u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) acc += in[i];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    acc = sh[threadIdx.x];
+    for (int o = 4; o > 0; o >>= 1) acc += __shfl_down_sync(0xffu, acc, o);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+  }
+}
+void launch_sum_all(Ctx& ctx, const double* in, u64 n, double* out_dev) {
+  int grid = (int)std::max<u64>(1, std::min<u64>((n + 255) / 256, (u64)ctx.sm_count * 8));
+  if (grid == 1) {
+    GTP_LAUNCH(ctx, k_sum_partial, 1, 256, 0, in, n, out_dev);
+    return;
+  }
+  BufP partial = ctx.alloc(grid);
+  GTP_LAUNCH(ctx, k_sum_partial, grid, 256, 0, in, n, partial->d);
+  GTP_LAUNCH(ctx, k_sum_partial, 1, 256, 0, partial->d, (u64)grid, out_dev);
+}
+
+// ------------------------------------------------------------------------------------------
+// classify: which axes v could be the linear axis of extract_linear (:275-294)?  A non-zero
+// element at multi-index idx rules out axis v unless idx is zero everywhere except possibly
+// idx[v] <= 1.  One pass builds the OR of the per-element "ruled out" masks; blocks stop early
+// once every axis is ruled out (dense operands bail out after their first tile).
+// ------------------------------------------------------------------------------------------
+struct ClsParams {
+  int ndim;
+  unsigned shape[MAXD];
+  long long str[MAXD];
+  u64 total;
+  unsigned all_mask;
+};
+__global__ void __launch_bounds__(256) k_classify(const double* __restrict__ in, const ClsParams p, Readback* rb) {
+  __shared__ unsigned sh_mask, sh_global;
+  if (threadIdx.x == 0) sh_mask = 0;
+  __syncthreads();
+  u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 base = (u64)blockIdx.x * blockDim.x; base < p.total; base += stride) {
+    if (threadIdx.x == 0) sh_global = *(volatile unsigned*)&rb->viol_mask;
+    __syncthreads();
+    if ((sh_global & p.all_mask) == p.all_mask) break;  // uniform: someone already ruled out every axis
+    u64 lin = base + threadIdx.x;
+    unsigned mask = 0;
+    if (lin < p.total) {
+      double x = in[lin];
+      if (x != 0.0) {
+        u64 rem = lin;
+        int nz_axis = -1, nz_count = 0;
+        unsigned nz_val = 0;
+        for (int d = p.ndim - 1; d >= 0; --d) {
+          unsigned i = (unsigned)(rem % p.shape[d]);
+          rem /= p.shape[d];
+          if (i != 0) {
+            nz_count++;
+            nz_axis = d;
+            nz_val = i;
+          }
+        }
+        if (nz_count >= 2) mask = p.all_mask;
+        else if (nz_count == 1) mask = (nz_val >= 2) ? p.all_mask : (p.all_mask & ~(1u << nz_axis));
+      }
+    }
+    if (mask) atomicOr(&sh_mask, mask);
+    __syncthreads();
+    unsigned m = sh_mask;
+    __syncthreads();
+    if ((m & p.all_mask) == p.all_mask) {
+      if (threadIdx.x == 0) atomicOr(&rb->viol_mask, m);
+      break;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && sh_mask) atomicOr(&rb->viol_mask, sh_mask);
+  // vals[0] = coeffs.first(); vals[1+v] = the candidate slope in[e_v] of axis v (:288-289)
+  if (blockIdx.x == 0 && threadIdx.x == 0) rb->vals[0] = in[0];
+  if (blockIdx.x == 0 && threadIdx.x < p.ndim)
+    rb->vals[1 + threadIdx.x] = p.shape[threadIdx.x] >= 2 ? in[p.str[threadIdx.x]] : 0.0;
+}
+void launch_classify(Ctx& ctx, const double* in, const Shape& shape, Readback* rb_dev) {
+  ClsParams p;
+  memset(&p, 0, sizeof(p));
+  p.ndim = (int)shape.size();
+  GTP_CHECK(p.ndim <= MAXD, GTP_ERR_ARG, "ndim exceeds GTP_MAX_NDIM");
+  p.total = prod(shape);
+  for (int d = 0; d < p.ndim; d++) p.shape[d] = (unsigned)shape[d];
+  {
+    long long st = 1;
+    for (int d = p.ndim - 1; d >= 0; --d) {
+      p.str[d] = st;
+      st *= (long long)shape[d];
+    }
+  }
+  p.all_mask = p.ndim >= 32 ? 0xffffffffu : ((1u << p.ndim) - 1u);
+  GTP_CUDA(cudaMemsetAsync(&rb_dev->viol_mask, 0, sizeof(unsigned), ctx.stream));
+  int grid = (int)std::max<u64>(1, std::min<u64>((p.total + 255) / 256, (u64)ctx.sm_count * 4));
+  GTP_LAUNCH(ctx, k_classify, grid, 256, 0, in, p, rb_dev);
+}
+
+__global__ void __launch_bounds__(256) k_eq(const double* __restrict__ a, const double* __restrict__ b, u64 n, Readback* rb) {
+  u64 stride = (u64)gridDim.x * blockDim.x;
+  bool ne = false;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) ne |= !(a[i] == b[i]);
+  if (__syncthreads_or(ne) && threadIdx.x == 0) rb->flag = 0;
+}
+void launch_eq(Ctx& ctx, const double* a, const double* b, u64 n, Readback* rb_dev) {
+  unsigned one = 1;
+  GTP_CUDA(cudaMemcpyAsync(&rb_dev->flag, &one, sizeof(unsigned), cudaMemcpyHostToDevice, ctx.stream));
+  int grid = (int)std::max<u64>(1, std::min<u64>((n + 255) / 256, (u64)ctx.sm_count * 8));
+  GTP_LAUNCH(ctx, k_eq, grid, 256, 0, a, b, n, rb_dev);
+}
+
+__global__ void k_gather_strided(const double* __restrict__ in, u64 stride, u64 len, u64 count, double* out) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = i < len ? in[i * stride] : 0.0;
+}
+void launch_gather_strided(Ctx& ctx, const double* in, u64 stride, u64 len, u64 count, double* out) {
+  if (count == 0) return;
+  GTP_LAUNCH(ctx, k_gather_strided, (unsigned)((count + 255) / 256), 256, 0, in, stride, len, count, out);
+}
+
+}  // namespace gtp

@@ -1,0 +1,227 @@
+// Truncated N-D Taylor product (multivariate_taylor.rs:972-1012) -- reference-order kernel,
+// kernel selection, MAC counting and the FP64 pipe probes.
+//
+// k_mul_ordered is the general kernel: any shapes, any row subset, one thread per output
+// coefficient.  It performs the multiply and the add separately (DMUL + DADD, no FMA) and
+// in exactly the reference's nesting order -- outer axes ascending, the innermost non-unit axis
+// summed from zero and then added (mul_1d :972-982 feeding `*z += o` :998) -- so its results are
+// bit-identical to the reference f64 path.  The register-tiled DFMA kernel for dense cubes lives in
+// kernels_mul_fast.cu; launch_mul() picks between them.
+#include "kernels.cuh"
+
+namespace gtp {
+
+constexpr int MUL_MAXE = 8;  // effective (non-unit) result axes handled with register odometers
+
+struct MulP {
+  int ne;                       // effective axes
+  int row_axis;                 // 1 if effective axis 0 is the (sharded) leading axis
+  unsigned xs[MAXD], ys[MAXD], rs[MAXD];
+  long long xstr[MAXD], ystr[MAXD];
+  u64 row_begin, row_step, row_count;
+  u64 row_elems;                // prod of rs over the non-row effective axes
+  u64 total;                    // outputs computed by this launch
+  const double* x;
+  const double* y;
+  double* out;
+  int accumulate;
+};
+
+template <int NE>
+__global__ void __launch_bounds__(128) k_mul_ordered(const MulP p) {
+  const u64 gstride = (u64)gridDim.x * blockDim.x;
+  for (u64 lin = (u64)blockIdx.x * blockDim.x + threadIdx.x; lin < p.total; lin += gstride) {
+    unsigned k[NE], lo[NE], hi[NE];
+    u64 rem = lin;
+    bool empty = false;
+#pragma unroll
+    for (int d = NE - 1; d >= 0; --d) {
+      if (d == 0 && p.row_axis) {
+        k[d] = (unsigned)(p.row_begin + rem * p.row_step);
+      } else {
+        k[d] = (unsigned)(rem % p.rs[d]);
+        rem /= p.rs[d];
+      }
+      unsigned l = (k[d] + 1 > p.ys[d]) ? k[d] + 1 - p.ys[d] : 0;   // :975 / :1002
+      unsigned h = (k[d] + 1 < p.xs[d]) ? k[d] + 1 : p.xs[d];       // :976 / :1003
+      lo[d] = l;
+      hi[d] = h;
+      empty |= (h <= l);
+    }
+    double total = p.accumulate ? p.out[lin] : 0.0;
+    if (!empty) {
+      unsigned j[NE];
+      long long xo = 0, yo = 0;
+#pragma unroll
+      for (int d = 0; d < NE - 1; d++) {
+        j[d] = lo[d];
+        xo += (long long)lo[d] * p.xstr[d];
+        yo += (long long)(k[d] - lo[d]) * p.ystr[d];
+      }
+      const long long xsl = p.xstr[NE - 1], ysl = p.ystr[NE - 1];
+      const unsigned kl = k[NE - 1], lol = lo[NE - 1], hil = hi[NE - 1];
+      while (true) {
+        // innermost non-unit axis: summed from zero, then added (mul_1d + `*z += o`)
+        double inner = 0.0;
+        const double* xp = p.x + xo + (long long)lol * xsl;
+        const double* yp = p.y + yo + (long long)(kl - lol) * ysl;
+        for (unsigned jl = lol; jl < hil; jl++) {
+          inner = __dadd_rn(inner, __dmul_rn(*xp, *yp));
+          xp += xsl;
+          yp -= ysl;
+        }
+        total = __dadd_rn(total, inner);
+        // odometer over the outer effective axes, last one fastest (the recursion order)
+        bool advanced = false;
+#pragma unroll
+        for (int dd = NE - 2; dd >= 0; --dd) {
+          if (!advanced) {
+            if (++j[dd] < hi[dd]) {
+              xo += p.xstr[dd];
+              yo -= p.ystr[dd];
+              advanced = true;
+            } else {
+              xo -= (long long)(hi[dd] - 1 - lo[dd]) * p.xstr[dd];
+              yo += (long long)(hi[dd] - 1 - lo[dd]) * p.ystr[dd];
+              j[dd] = lo[dd];
+            }
+          }
+        }
+        if (!advanced) break;  // wrapped around every axis (or NE == 1)
+      }
+    }
+    p.out[lin] = total;
+  }
+}
+
+double mul_macs(const Shape& xs, const Shape& ys, const Shape& rs) {
+  double total = 1.0;
+  for (size_t a = 0; a < rs.size(); a++) {
+    double s = 0;
+    for (u64 k = 0; k < rs[a]; k++) {
+      u64 lo = sat_sub(k + 1, ys[a]), hi = std::min<u64>(k + 1, xs[a]);
+      if (hi > lo) s += (double)(hi - lo);
+    }
+    total *= s;
+  }
+  return total;
+}
+
+// implemented in kernels_mul_fast.cu
+bool fast_mul_applicable(const Ctx& ctx, const MulArgs& a);
+void launch_mul_fast(Ctx& ctx, const MulArgs& a);
+
+int mul_kernel_kind(const Ctx& ctx, const MulArgs& a) { return (ctx.fast_mul && fast_mul_applicable(ctx, a)) ? 1 : 0; }
+
+static void launch_mul_ordered(Ctx& ctx, const MulArgs& a) {
+  const int nd = a.ndim;
+  GTP_CHECK(nd <= MAXD, GTP_ERR_ARG, "ndim exceeds GTP_MAX_NDIM");
+  MulP p;
+  memset(&p, 0, sizeof(p));
+  Shape xst(nd, 1), yst(nd, 1);
+  for (int i = nd - 2; i >= 0; --i) {
+    xst[i] = xst[i + 1] * a.xs[i + 1];
+    yst[i] = yst[i + 1] * a.ys[i + 1];
+  }
+  u64 row_elems = 1;
+  for (int i = 1; i < nd; i++) row_elems *= a.rs[i];
+  int ne = 0;
+  p.row_axis = 0;
+  for (int d = 0; d < nd; d++) {
+    bool is_row = (d == 0);
+    if (a.rs[d] == 1) {
+      if (is_row) GTP_CHECK(a.row_count <= 1 && a.row_begin == 0, GTP_ERR_ARG, "row range on a unit leading axis");
+      continue;  // unit result axis: only index 0 of both operands contributes
+    }
+    GTP_CHECK(ne < MUL_MAXE, GTP_ERR_ARG, "more than 8 non-unit result axes are not supported yet");
+    if (is_row) p.row_axis = 1;
+    p.xs[ne] = (unsigned)a.xs[d];
+    p.ys[ne] = (unsigned)a.ys[d];
+    p.rs[ne] = (unsigned)a.rs[d];
+    p.xstr[ne] = (long long)xst[d];
+    p.ystr[ne] = (long long)yst[d];
+    ne++;
+  }
+  if (ne == 0) {  // single coefficient: leaf `*res += x*y` (:988-991)
+    p.xs[0] = p.ys[0] = p.rs[0] = 1;
+    p.xstr[0] = p.ystr[0] = 1;
+    ne = 1;
+  }
+  p.ne = ne;
+  p.row_begin = a.row_begin;
+  p.row_step = a.row_step;
+  p.row_count = (nd == 0 || a.rs[0] == 1) ? 1 : a.row_count;
+  p.row_elems = (nd == 0) ? 1 : row_elems;
+  p.total = p.row_count * p.row_elems;
+  p.x = a.x;
+  p.y = a.y;
+  p.out = a.out;
+  p.accumulate = a.accumulate ? 1 : 0;
+  if (p.total == 0) return;
+  int block = 128;
+  int grid = (int)std::max<u64>(1, std::min<u64>((p.total + block - 1) / block, (u64)ctx.sm_count * 64));
+  switch (ne) {
+#define CASE(N) case N: GTP_LAUNCH(ctx, k_mul_ordered<N>, grid, block, 0, p); break;
+    CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+#undef CASE
+  }
+}
+
+void launch_mul(Ctx& ctx, const MulArgs& a) {
+  if (mul_kernel_kind(ctx, a) == 1) launch_mul_fast(ctx, a);
+  else launch_mul_ordered(ctx, a);
+}
+
+// ------------------------------------------------------------------------------------------
+// FP64 pipe probes: the denominators of the product roofline, measured not quoted.
+//   kind 0: DFMA, 8 independent chains per thread, every SM saturated
+//   kind 1: DMMA  mma.sync.aligned.m8n8k4.f64, 4 independent accumulator tiles per warp
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_probe_dfma(int iters, double seed, double* sink) {
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (s == 12345.678) sink[0] = s;
+}
+__global__ void __launch_bounds__(256) k_probe_dmma(int iters, double seed, double* sink) {
+  double a = seed + (threadIdx.x & 31) * 1e-3, b = 1.0 + (threadIdx.x & 7) * 1e-6;
+  double c0 = 0, c1 = 0, d0 = 0, d1 = 0, e0 = 0, e1 = 0, f0 = 0, f1 = 0;
+  for (int i = 0; i < iters; i++) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(e0), "+d"(e1) : "d"(a), "d"(b));
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(f0), "+d"(f1) : "d"(a), "d"(b));
+  }
+  double s = c0 + c1 + d0 + d1 + e0 + e1 + f0 + f1;
+  if (s == 12345.678) sink[0] = s;
+}
+
+void fp64_peak_probe(Ctx& ctx, int kind, int iters, double* flops, double* ms) {
+  BufP sink = ctx.alloc(1);
+  int grid = ctx.sm_count * 8, block = 256;
+  cudaEvent_t e0, e1;
+  GTP_CUDA(cudaEventCreate(&e0));
+  GTP_CUDA(cudaEventCreate(&e1));
+  for (int rep = 0; rep < 2; rep++) {  // first pass warms up
+    GTP_CUDA(cudaEventRecord(e0, ctx.stream));
+    if (kind == 0) GTP_LAUNCH(ctx, k_probe_dfma, grid, block, 0, iters, 1.0, sink->d);
+    else GTP_LAUNCH(ctx, k_probe_dmma, grid, block, 0, iters, 1.0, sink->d);
+    GTP_CUDA(cudaEventRecord(e1, ctx.stream));
+    GTP_CUDA(cudaEventSynchronize(e1));
+  }
+  float t = 0;
+  GTP_CUDA(cudaEventElapsedTime(&t, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  double threads = (double)grid * block;
+  double f = (kind == 0) ? threads * (double)iters * 8.0 * 2.0
+                         : (threads / 32.0) * (double)iters * 4.0 * (8.0 * 8.0 * 4.0) * 2.0;
+  *ms = t;
+  *flops = f / (t * 1e-3);
+}
+
+}  // namespace gtp

@@ -1,0 +1,175 @@
+/*
+ * genfer_taylor.h -- C ABI of libgenfer_taylor.so, the B200 (sm_100a) implementation of genfer's
+ * dense truncated Taylor arithmetic for the f64 Number path.
+ *
+ * The reference (fzaiser/genfer, pure Rust) has no FFI layer: its boundary for this path is the
+ * generic value type `TaylorPoly<T: Number>` (src/multivariate_taylor.rs:13-19) with
+ * `impl Add/Sub/Mul/Div/Neg` (:854-1237) plus ~25 inherent methods, and the univariate
+ * `TaylorExpansion<T>` (src/univariate_taylor.rs:9-13, `impl Number` :150-211).  Each entry point
+ * below replaces one of those for T = F64 and cites it.  A Rust `extern "C"` shim that binds these
+ * (rust/genfer-taylor-sys) and the patch to multivariate_taylor.rs are shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only.  Handles are opaque.  All functions return a gtp_status
+ *    (0 = ok); `gtp_last_error(ctx)` gives the message.  Where the reference would panic
+ *    (assert!/index out of bounds) the call returns GTP_ERR_INDEX and the Rust shim panics.
+ *  - Element type is IEEE-754 binary64.  Buffers are dense, row-major over the STORED shape
+ *    (`coeffs.shape()`), last variable fastest, base pointer >= 256-byte aligned.  The conceptual
+ *    truncation `degrees_p1` is host metadata; GTP_UNBOUNDED (= usize::MAX) means "exact
+ *    polynomial, no truncation" (generating_function.rs:485, :569).
+ *  - Value semantics like the reference: every operation returns a NEW handle and never mutates
+ *    or aliases-for-write its inputs (buffers are immutable and reference counted, so clone is O(1);
+ *    the reference deep-copies, multivariate_taylor.rs:10-12).  The caller frees every handle.
+ *  - One context = one CUDA device + one stream.  Calls on one context are not re-entrant
+ *    (the reference is single threaded, src/main.rs:96-106).  Launches are asynchronous; only the
+ *    scalar readers and gtp_to_host synchronise.  Operator dispatch needs a few data-dependent
+ *    predicates (is_zero / is_one / extract_linear, multivariate_taylor.rs:1021-1061): these are
+ *    evaluated by a device kernel and cached per handle.
+ *  - There is NO CPU fallback: if no CUDA device is present gtp_ctx_create fails with GTP_ERR_CUDA.
+ */
+#ifndef GENFER_TAYLOR_H
+#define GENFER_TAYLOR_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GTP_UNBOUNDED UINT64_MAX /* Rust usize::MAX */
+#define GTP_MAX_NDIM 24
+
+typedef enum gtp_status {
+  GTP_OK = 0,
+  GTP_ERR_INDEX = 1, /* the reference's assert!/panic on a bad variable / order / index   */
+  GTP_ERR_SHAPE = 2, /* violated shape/degree invariant (check_invariants, :23-31)         */
+  GTP_ERR_OOM = 3,   /* device allocation failed                                           */
+  GTP_ERR_CUDA = 4,  /* CUDA runtime / launch error, or no device                          */
+  GTP_ERR_ARG = 5    /* null pointer, ndim > GTP_MAX_NDIM, ...                              */
+} gtp_status;
+
+typedef struct gtp_ctx gtp_ctx;   /* device + stream + stream-ordered pool + pinned read-back page */
+typedef struct gtp_poly gtp_poly; /* TaylorPoly<F64>  (multivariate_taylor.rs:13-19)              */
+typedef struct gtu_series gtu_series; /* TaylorExpansion<F64> (univariate_taylor.rs:9-13)         */
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* `cuda_stream` may be NULL (the context creates its own non-blocking stream) or an existing
+ * cudaStream_t (e.g. torch's current stream) to interleave with the caller's work. */
+int gtp_ctx_create(int device, void* cuda_stream, gtp_ctx** out);
+void gtp_ctx_destroy(gtp_ctx* ctx);
+const char* gtp_last_error(gtp_ctx* ctx);
+int gtp_ctx_synchronize(gtp_ctx* ctx);
+void* gtp_ctx_stream(gtp_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t gtp_ctx_launch_count(gtp_ctx* ctx);
+/* tuning knob: 0 = always use the generic product kernel, 1 = allow the register-tiled one */
+int gtp_ctx_set_fast_mul(gtp_ctx* ctx, int enabled);
+
+/* ---- construction, transfer, metadata ------------------------------------------------------- */
+/* TaylorPoly::new (:33-41): upload `data` (row-major over `shape`, prod(shape) doubles). */
+int gtp_from_host(gtp_ctx* ctx, int ndim, const uint64_t* shape, const uint64_t* degrees_p1,
+                  const double* data, gtp_poly** out);
+/* Same, but wraps an existing device buffer WITHOUT copying or taking ownership (the caller keeps
+ * it alive while the handle or anything cloned from it lives).  Used for NCCL-gathered operands. */
+int gtp_from_device(gtp_ctx* ctx, int ndim, const uint64_t* shape, const uint64_t* degrees_p1,
+                    const double* device_data, gtp_poly** out);
+int gtp_to_host(gtp_ctx* ctx, const gtp_poly* p, double* out); /* into_array (:63-66); synchronises */
+int gtp_device_ptr(gtp_ctx* ctx, const gtp_poly* p, const double** out);
+int gtp_clone(gtp_ctx* ctx, const gtp_poly* p, gtp_poly** out); /* Clone (:10) */
+void gtp_free(gtp_ctx* ctx, gtp_poly* p);
+int gtp_ndim(const gtp_poly* p);                      /* num_vars (:48-51)            */
+uint64_t gtp_len(const gtp_poly* p);                  /* coeffs.len()                 */
+void gtp_shape(const gtp_poly* p, uint64_t* out);     /* coeffs.shape() (stored)      */
+void gtp_degrees_p1(const gtp_poly* p, uint64_t* out);/* shape() (:53-56)             */
+
+int gtp_from_scalar(gtp_ctx* ctx, double x, gtp_poly** out);                              /* From<T> :626-630, Zero/One :638-656 */
+int gtp_zero_with(gtp_ctx* ctx, int ndim, const uint64_t* degrees_p1, gtp_poly** out);     /* :208-216 */
+int gtp_var(gtp_ctx* ctx, uint64_t v, double x, uint64_t len, gtp_poly** out);            /* :239-248 */
+int gtp_var_at_zero(gtp_ctx* ctx, uint64_t v, uint64_t len, gtp_poly** out);              /* :228-237 */
+int gtp_var_with_degrees_p1(gtp_ctx* ctx, uint64_t v, double x, int ndim, const uint64_t* degrees_p1,
+                            gtp_poly** out);                                               /* :250-259 */
+
+/* ---- operators (impl Add/Sub/Mul/Div/Neg, full reference dispatch order) --------------------- */
+int gtp_add(gtp_ctx* ctx, const gtp_poly* a, const gtp_poly* b, gtp_poly** out); /* :854-882   */
+int gtp_sub(gtp_ctx* ctx, const gtp_poly* a, const gtp_poly* b, gtp_poly** out); /* :911-937   */
+int gtp_mul(gtp_ctx* ctx, const gtp_poly* a, const gtp_poly* b, gtp_poly** out); /* :1014-1072 */
+int gtp_div(gtp_ctx* ctx, const gtp_poly* a, const gtp_poly* b, gtp_poly** out); /* :1194-1231 */
+int gtp_neg(gtp_ctx* ctx, const gtp_poly* a, gtp_poly** out);                    /* :902-909   */
+int gtp_exp(gtp_ctx* ctx, const gtp_poly* a, gtp_poly** out);                    /* :406-417, :1271-1317 */
+int gtp_log(gtp_ctx* ctx, const gtp_poly* a, gtp_poly** out);                    /* :419-430, :1319-1386 */
+int gtp_pow(gtp_ctx* ctx, const gtp_poly* a, uint32_t exp, gtp_poly** out);      /* :433-451   */
+
+/* ---- gathers, shifts, reductions -------------------------------------------------------------- */
+int gtp_derivative(gtp_ctx* ctx, const gtp_poly* a, uint64_t v, uint64_t n, gtp_poly** out);                /* :457-481 */
+int gtp_taylor_expansion_of_coeff(gtp_ctx* ctx, const gtp_poly* a, uint64_t v, uint64_t n, gtp_poly** out); /* :484-509 */
+int gtp_shift_down(gtp_ctx* ctx, const gtp_poly* a, uint64_t v, uint64_t n, gtp_poly** out);                /* :514-536 */
+int gtp_coefficients_of_term(gtp_ctx* ctx, const gtp_poly* a, uint64_t v, uint64_t order, gtp_poly** out);  /* :341-358 */
+int gtp_taylor_polynomial(gtp_ctx* ctx, const gtp_poly* a, uint64_t v, uint64_t order, gtp_poly** out);     /* :360-378 */
+int gtp_taylor_polynomial_terms(gtp_ctx* ctx, const gtp_poly* a, uint64_t v, const uint64_t* orders,
+                                int n_orders, gtp_poly** out);                                              /* :380-404 */
+int gtp_subst_var(gtp_ctx* ctx, const gtp_poly* a, uint64_t v, const gtp_poly* subst, gtp_poly** out);      /* :540-580 */
+int gtp_truncate_to_degree_p1(gtp_ctx* ctx, const gtp_poly* a, uint64_t degree_p1, gtp_poly** out);         /* :183-193 */
+int gtp_remove_last_variable(gtp_ctx* ctx, const gtp_poly* a, gtp_poly** out);                              /* :172-181 */
+int gtp_extend_to_dim(gtp_ctx* ctx, const gtp_poly* a, uint64_t ndim, uint64_t degree_p1, gtp_poly** out);  /* :81-89   */
+/* test helper `extend` (:91-112): zero-extend the stored array to `new_size`, degrees = new_size */
+int gtp_extend(gtp_ctx* ctx, const gtp_poly* a, int ndim, const uint64_t* new_size, gtp_poly** out);
+
+/* ---- scalar readers (synchronise) ------------------------------------------------------------ */
+int gtp_constant_term(gtp_ctx* ctx, const gtp_poly* a, double* out);                                  /* :296-299 */
+int gtp_coefficient(gtp_ctx* ctx, const gtp_poly* a, const uint64_t* index, int n_index, double* out);/* :314-339 */
+/* The callers' read-back pattern (generating_function.rs:959-965, :988-993): `count` coefficients
+ * along axis v with every other index 0, as ONE gather kernel + ONE D2H copy. */
+int gtp_gather_axis(gtp_ctx* ctx, const gtp_poly* a, uint64_t v, uint64_t count, double* out);
+int gtp_extract_constant(gtp_ctx* ctx, const gtp_poly* a, int* is_constant, double* value);           /* :262-269 */
+/* :275-294.  *is_linear = 1 and (c, m, v) filled when the polynomial is c + m*eps_v. */
+int gtp_extract_linear(gtp_ctx* ctx, const gtp_poly* a, int* is_linear, double* c, double* m, uint64_t* v);
+int gtp_is_zero(gtp_ctx* ctx, const gtp_poly* a, int* out);                                           /* :643-645 */
+int gtp_is_one(gtp_ctx* ctx, const gtp_poly* a, int* out);                                            /* :653-655 */
+int gtp_evaluate_all_one(gtp_ctx* ctx, const gtp_poly* a, double* out);                               /* :583-586 */
+/* derive(PartialEq) (:10): stored shape, degrees_p1 and every coefficient (IEEE ==). */
+int gtp_eq(gtp_ctx* ctx, const gtp_poly* a, const gtp_poly* b, int* out);
+
+/* ---- the hot kernel, exposed raw for the bench and for output-axis sharding ------- */
+/* General truncated N-D product `mul` (:984-1012), no dispatch.  Computes the leading-axis output
+ * rows k0 = row_begin + i*row_step, i < row_count, of the result of shape `rshape` and writes row i
+ * (prod(rshape[1:]) doubles) at out_rows + i*prod(rshape[1:]).  x, y are device buffers of shapes
+ * xshape / yshape.  With row_begin = rank, row_step = world this is one rank's cyclic shard. */
+int gtp_mul_rows_raw(gtp_ctx* ctx, int ndim, const uint64_t* xshape, const double* x,
+                     const uint64_t* yshape, const double* y, const uint64_t* rshape,
+                     uint64_t row_begin, uint64_t row_step, uint64_t row_count, double* out_rows);
+/* MAC count of the general product (trip counts of :975-977 and :1002-1004); FLOPs = 2*MACs. */
+double gtp_mul_macs(int ndim, const uint64_t* xshape, const uint64_t* yshape, const uint64_t* rshape);
+/* Which kernel gtp_mul_rows_raw would pick for these shapes: 0 generic, 1 register-tiled. */
+int gtp_mul_kernel_kind(gtp_ctx* ctx, int ndim, const uint64_t* xshape, const uint64_t* yshape,
+                        const uint64_t* rshape);
+/* FP64 pipe microbenchmarks (the roofline denominator): runs `iters` dependent-chain DFMA (kind 0)
+ * or DMMA m8n8k4 (kind 1) per thread on a full grid and returns achieved FLOP/s in *flops. */
+int gtp_fp64_peak_probe(gtp_ctx* ctx, int kind, int iters, double* flops, double* ms);
+
+/* ---- univariate TaylorExpansion<F64> (src/univariate_taylor.rs) -------------------------------- */
+int gtu_constant(gtp_ctx* ctx, double x, gtu_series** out);                           /* Constant(T) :11, From<u32> :262-266 */
+int gtu_from_coefficients(gtp_ctx* ctx, const double* xs, uint64_t n, gtu_series** out); /* :62-66 */
+int gtu_var(gtp_ctx* ctx, double x, uint64_t order, gtu_series** out);                /* :16-23   */
+void gtu_free(gtp_ctx* ctx, gtu_series* s);
+int gtu_is_constant(const gtu_series* s);
+uint64_t gtu_order(const gtu_series* s);                                              /* :38-43 (GTP_UNBOUNDED for Constant) */
+int gtu_to_host(gtp_ctx* ctx, const gtu_series* s, double* out);                      /* order() doubles (1 for Constant) */
+int gtu_coeff(gtp_ctx* ctx, const gtu_series* s, uint64_t order, double* out);        /* :25-36   */
+int gtu_derivative(gtp_ctx* ctx, const gtu_series* s, uint64_t order, double* out);   /* :45-60   */
+int gtu_add(gtp_ctx* ctx, const gtu_series* a, const gtu_series* b, gtu_series** out);/* :268-306 */
+int gtu_sub(gtp_ctx* ctx, const gtu_series* a, const gtu_series* b, gtu_series** out);/* :321-362 */
+int gtu_mul(gtp_ctx* ctx, const gtu_series* a, const gtu_series* b, gtu_series** out);/* :364-389 */
+int gtu_div(gtp_ctx* ctx, const gtu_series* a, const gtu_series* b, gtu_series** out);/* :397-439 */
+int gtu_neg(gtp_ctx* ctx, const gtu_series* a, gtu_series** out);                     /* :308-319 */
+int gtu_exp(gtp_ctx* ctx, const gtu_series* a, gtu_series** out);                     /* :151-168 */
+int gtu_log(gtp_ctx* ctx, const gtu_series* a, gtu_series** out);                     /* :170-189 */
+int gtu_pow(gtp_ctx* ctx, const gtu_series* a, uint32_t exp, gtu_series** out);       /* :192-203 */
+int gtu_subst(gtp_ctx* ctx, const gtu_series* a, const gtu_series* subst, gtu_series** out); /* :93-115 */
+int gtu_taylor_expansion_of_coeff(gtp_ctx* ctx, const gtu_series* a, uint64_t n, gtu_series** out); /* :69-89 */
+int gtu_eq(gtp_ctx* ctx, const gtu_series* a, const gtu_series* b, int* out);         /* derive(PartialEq) :8 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GENFER_TAYLOR_H */

@@ -697,10 +697,11 @@ template <class T> T unrolled_sum(const T* xs, usize n) {
   for (usize i = 0; i < n; i++) acc = acc + xs[i];
   return acc;
 }
-// ndarray 0.15.6 ArrayBase::sum_axis: if `axis` is the minimum-stride axis, each lane is
-// summed with unrolled_fold; otherwise `res = zeros; for subview in axis_iter: res = res + subview`.
-// For a row-major array the min-stride axis is the last axis with length > 1 (ties: ndarray's
-// min_stride_axis scans from the last axis and keeps the first minimum it sees).
+// ndarray 0.15.6 ArrayBase::sum_axis: if `axis` is the minimum-stride axis, each lane is summed
+// with unrolled_fold; otherwise `res = zeros; for subview in axis_iter(axis): res = res + subview`.
+// Dimension::min_stride_axis scans the axes in REVERSE order and keeps the first minimum of
+// |stride| (unit axes are not skipped), so for a standard row-major array it is always the LAST
+// axis (stride 1).
 template <class T> Arr<T> sum_axis(const Arr<T>& a, usize axis) {
   std::vector<usize> rshape = a.shape;
   rshape.erase(rshape.begin() + axis);
@@ -708,28 +709,8 @@ template <class T> Arr<T> sum_axis(const Arr<T>& a, usize axis) {
   usize outer = 1, inner = 1, len = a.shape[axis];
   for (usize i = 0; i < axis; i++) outer *= a.shape[i];
   for (usize i = axis + 1; i < a.ndim(); i++) inner *= a.shape[i];
-  // min-stride axis of a standard-layout array (ndarray dimension::min_stride_axis):
-  usize min_axis = a.ndim() - 1;
-  {
-    // strides (elements) of the standard layout
-    std::vector<usize> st(a.ndim(), 1);
-    for (usize i = a.ndim() - 1; i-- > 0;) st[i] = st[i + 1] * a.shape[i + 1];
-    usize best = UMAX;
-    for (usize i = a.ndim(); i-- > 0;) {
-      if (a.shape[i] > 1 && st[i] < best) { best = st[i]; min_axis = i; }
-    }
-  }
-  if (axis == min_axis && inner == 1) {
+  if (axis == a.ndim() - 1) {
     for (usize o = 0; o < outer; o++) res.data[o] = unrolled_sum(a.data.data() + o * len, len);
-  } else if (axis == min_axis) {
-    // lane is strided (trailing unit axes only happen with inner==1, so this is unreachable for
-    // standard layouts; kept for completeness: strided lanes fall back to a plain fold)
-    for (usize o = 0; o < outer; o++)
-      for (usize in = 0; in < inner; in++) {
-        T acc = Num<T>::zero();
-        for (usize l = 0; l < len; l++) acc = acc + a.data[(o * len + l) * inner + in];
-        res.data[o * inner + in] = acc;
-      }
   } else {
     for (usize l = 0; l < len; l++)
       for (usize o = 0; o < outer; o++)

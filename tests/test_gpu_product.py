@@ -1,0 +1,135 @@
+"""GPU parity of the hot kernel: the truncated N-D product (multivariate_taylor.rs:972-1012).
+
+ * mid sizes: every kernel variant against the oracle on seeded dense tensors (distributions U and P of
+   SURVEY 8d), ragged shapes, row subsets (the sharding primitive)
+ * BASELINE sizes ((4,32) ... (6,16)): size-independent properties -- separable operands have a
+   closed-form product (outer product of 1-D truncated convolutions), commutativity, linearity
+"""
+import numpy as np
+import pytest
+
+from helpers import RTOL, synth_pgf, synth_uniform
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import genfer_b200
+    c = genfer_b200.Context(0)
+    genfer_b200.set_default_context(c)
+    yield c
+    genfer_b200.set_default_context(None)
+    c.close()
+
+
+def gpu_mul_raw(ctx, x, y, rshape, rows=None, fast=True):
+    """Calls gtp_mul_rows_raw through the C ABI on torch-owned device buffers."""
+    import torch
+    ctx.set_fast_mul(fast)
+    xd = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    yd = torch.from_numpy(np.ascontiguousarray(y)).cuda()
+    if rows is None:
+        begin, step, count = 0, 1, rshape[0]
+    else:
+        begin, step, count = rows
+    out = torch.full((count,) + tuple(rshape[1:]), float("nan"), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    ctx.mul_rows_raw(x.shape, xd.data_ptr(), y.shape, yd.data_ptr(), rshape, begin, step, count, out.data_ptr())
+    ctx.synchronize()
+    ctx.set_fast_mul(True)
+    return out.cpu().numpy()
+
+
+def rel_err(a, b):
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+
+
+CUBES = [(2, 16), (3, 16), (4, 8), (3, 32), (2, 32), (4, 12), (5, 8), (3, 24), (6, 4)]
+
+
+@pytest.mark.parametrize("n,d", CUBES)
+@pytest.mark.parametrize("dist", ["U", "P"])
+def test_cube_product_matches_oracle(ctx, n, d, dist):
+    from oracle import oracle as O
+    gen = synth_uniform if dist == "U" else synth_pgf
+    x, y = gen((d,) * n, 20230517), gen((d,) * n, 20231210)
+    ref = O.mul_raw(x, y, (d,) * n)
+    exact = gpu_mul_raw(ctx, x, y, (d,) * n, fast=False)
+    assert np.array_equal(exact.view(np.uint64), ref.view(np.uint64)), "reference-order kernel must be bit-exact"
+    fast = gpu_mul_raw(ctx, x, y, (d,) * n, fast=True)
+    assert rel_err(fast, ref) <= RTOL, rel_err(fast, ref)   # all-positive inputs: no cancellation
+
+
+RAGGED = [((3, 5), (4, 2), (6, 6)), ((3, 5), (4, 2), (5, 4)), ((1, 7), (6, 1), (6, 7)), ((4, 4, 4), (2, 1, 3), (5, 4, 6)),
+          ((16, 16), (16, 16), (16, 9)), ((16, 16, 16), (5, 16, 16), (16, 16, 16)), ((9,), (5,), (11,)),
+          ((2, 3, 4, 5), (5, 4, 3, 2), (6, 6, 6, 6)), ((8, 16), (16, 16), (16, 16))]
+
+
+@pytest.mark.parametrize("xs,ys,rs", RAGGED)
+def test_ragged_product_matches_oracle(ctx, xs, ys, rs):
+    from oracle import oracle as O
+    rng = np.random.default_rng(3)
+    x, y = rng.standard_normal(xs), rng.standard_normal(ys)
+    ref = O.mul_raw(x, y, rs)
+    got = gpu_mul_raw(ctx, x, y, rs, fast=False)
+    assert np.array_equal(got.view(np.uint64), ref.view(np.uint64))
+    got = gpu_mul_raw(ctx, x, y, rs, fast=True)
+    np.testing.assert_allclose(got, ref, rtol=1e-11, atol=1e-12)
+
+
+@pytest.mark.parametrize("n,d,world", [(3, 16, 2), (4, 8, 4), (3, 16, 8), (4, 16, 8)])
+def test_row_shards_tile_the_product(ctx, n, d, world):
+    """Cyclic leading-axis shards computed independently reassemble the full product."""
+    x, y = synth_uniform((d,) * n, 1), synth_uniform((d,) * n, 2)
+    full = gpu_mul_raw(ctx, x, y, (d,) * n)
+    out = np.empty_like(full)
+    for r in range(world):
+        cnt = len(range(r, d, world))
+        out[r::world] = gpu_mul_raw(ctx, x, y, (d,) * n, rows=(r, world, cnt))
+    assert np.array_equal(out.view(np.uint64), full.view(np.uint64))
+
+
+def conv1d_trunc(a, b, n):
+    return np.convolve(a, b)[:n]
+
+
+@pytest.mark.parametrize("n,d", [(4, 32), (5, 16), (6, 12), (5, 24), (6, 16)])
+def test_baseline_sizes_separable_closed_form(ctx, n, d):
+    """At BASELINE's sizes: X = (x)_a, Y = (y)_a outer products  =>  X*Y = outer product of the 1-D truncated
+    convolutions.  Checks every coefficient of the full-size product without a CPU N-D reference."""
+    import torch
+    rng = np.random.default_rng(n * 100 + d)
+    xa = [rng.uniform(0.5, 1.5, d) for _ in range(n)]
+    ya = [rng.uniform(0.5, 1.5, d) for _ in range(n)]
+
+    def outer(vs):
+        t = torch.ones((), dtype=torch.float64, device="cuda")
+        for v in vs:
+            t = t.unsqueeze(-1) * torch.from_numpy(v).cuda()
+        return t.contiguous()
+    X, Y = outer(xa), outer(ya)
+    Z = torch.empty_like(X)
+    torch.cuda.synchronize()
+    ctx.mul_rows_raw(X.shape, X.data_ptr(), Y.shape, Y.data_ptr(), X.shape, 0, 1, d, Z.data_ptr())
+    ctx.synchronize()
+    expect = outer([conv1d_trunc(xa[i], ya[i], d) for i in range(n)])
+    err = torch.max(torch.abs(Z - expect) / expect).item()
+    assert err <= 1e-12, err
+    # commutativity on the same operands
+    Z2 = torch.empty_like(X)
+    ctx.mul_rows_raw(Y.shape, Y.data_ptr(), X.shape, X.data_ptr(), X.shape, 0, 1, d, Z2.data_ptr())
+    ctx.synchronize()
+    assert torch.max(torch.abs(Z2 - Z) / Z).item() <= 1e-12
+
+
+def test_operator_level_product_uses_fast_kernel(ctx):
+    """TaylorPoly * TaylorPoly on dense cubes goes through the full dispatch into the tiled kernel."""
+    import genfer_b200
+    from oracle import oracle as O
+    d, n = 16, 3
+    x, y = synth_pgf((d,) * n, 5), synth_pgf((d,) * n, 6)
+    g = genfer_b200.taylor(x) * genfer_b200.taylor(y)
+    o = O.taylor(x) * O.taylor(y)
+    assert g.array_shape() == o.array_shape() and g.shape() == o.shape()
+    assert rel_err(g.array(), o.array()) <= RTOL

@@ -1,0 +1,354 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against
+(a) the literal vectors of the reference's unit tests and (b) the CPU oracle on seeded random inputs.
+
+Bars: integer work (stored shapes, degrees_p1) bit-exact everywhere; f64 coefficients bit-exact for
+the element-wise/gather family, the reference-order product kernel and the single-axis division;
+within 1e-12 relative (north_star) wherever the summation order or libm differs (exp/log, the
+register-tiled product, general division).
+"""
+import numpy as np
+import pytest
+
+from helpers import RTOL, assert_close, assert_meta_equal, assert_same, to_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def G():
+    import genfer_b200
+    ctx = genfer_b200.Context(0)
+    genfer_b200.set_default_context(ctx)
+    yield genfer_b200
+    genfer_b200.set_default_context(None)
+    ctx.close()
+
+
+def O():
+    from oracle import oracle
+    return oracle
+
+
+def both(G, a, degrees=None):
+    a = np.asarray(a, dtype=np.float64)
+    d = a.shape if degrees is None else degrees
+    return G.TaylorPoly.new(a, d), O().TaylorPoly.new(a, d)
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's own unit tests, on the device
+# ---------------------------------------------------------------------------------------------
+def test_ref_2d_derivative(G):
+    """multivariate_taylor.rs:733-772"""
+    t = G.taylor([[1.0, 2.0, 3.0, 4.0], [5.0, 6.0, 7.0, 8.0], [9.0, 10.0, 11.0, 12.0], [13.0, 14.0, 15.0, 16.0]])
+    assert t.derivative(0, 1) == G.taylor([[5.0, 6.0, 7.0, 8.0], [18.0, 20.0, 22.0, 24.0], [39.0, 42.0, 45.0, 48.0]])
+    assert t.derivative(1, 1) == G.taylor([[2.0, 6.0, 12.0], [6.0, 14.0, 24.0], [10.0, 22.0, 36.0], [14.0, 30.0, 48.0]])
+    assert t.derivative(0, 2) == t.derivative(0, 1).derivative(0, 1)
+    assert t.derivative(1, 2) == t.derivative(1, 1).derivative(1, 1)
+    assert t.derivative(0, 3) == t.derivative(0, 1).derivative(0, 1).derivative(0, 1)
+
+
+def test_ref_2d_taylor_expansion_of_coeff(G):
+    """multivariate_taylor.rs:775-803"""
+    t = G.taylor([[1.0, 2.0, 3.0, 4.0], [5.0, 6.0, 7.0, 8.0], [9.0, 10.0, 11.0, 12.0], [13.0, 14.0, 15.0, 16.0]])
+    assert t.taylor_expansion_of_coeff(0, 2) == G.taylor([[9.0, 10.0, 11.0, 12.0], [39.0, 42.0, 45.0, 48.0]])
+    assert t.taylor_expansion_of_coeff(1, 3) == G.taylor([[4.0], [8.0], [12.0], [16.0]])
+    expected = G.taylor([[11.0, 36.0], [45.0, 144.0]])
+    assert t.taylor_expansion_of_coeff(0, 2).taylor_expansion_of_coeff(1, 2) == expected
+    assert t.taylor_expansion_of_coeff(1, 2).taylor_expansion_of_coeff(0, 2) == expected
+
+
+def test_ref_2d_subst_var(G):
+    """multivariate_taylor.rs:806-829"""
+    t = G.taylor([[1.0, 2.0, 3.0], [4.0, 5.0, 6.0], [7.0, 8.0, 9.0]])
+    s = G.taylor([[10.0, 11.0, 12.0], [13.0, 14.0, 15.0], [16.0, 17.0, 18.0]])
+    assert t.subst_var(0, s) == G.taylor([[741.0, 2436.0, 5353.0], [1872.0, 6163.0, 13516.0], [3487.0, 11452.0, 25030.0]])
+    assert t.subst_var(1, s) == G.taylor([[321.0, 682.0, 1107.0], [1460.0, 3101.0, 5016.0], [4111.0, 8736.0, 14088.0]])
+    assert t.subst_var(0, s).subst_var(1, s) != t.subst_var(1, s).subst_var(0, s)
+
+
+@pytest.mark.parametrize("op", ["add", "sub", "mul", "div"])
+def test_ref_mismatched_shapes(G, op):
+    """multivariate_taylor.rs:885-892, :940-947, :1081-1094, :1240-1253"""
+    T = G.TaylorPoly
+    f = {"add": lambda x, y: x + y, "sub": lambda x, y: x - y, "mul": lambda x, y: x * y, "div": lambda x, y: x / y}[op]
+    a, b = T.var(0, 1.0, 5), T.var(1, 1.0, 4)
+    assert f(a, b).extend([5, 4]) == f(a.extend([5, 4]), b.extend([5, 4]))
+    c, d = a * a * a, b * b
+    assert (c * d).extend([5, 4]) == c.extend([5, 4]) * d.extend([5, 4])
+
+
+def test_ref_2d_mul_and_const(G):
+    """multivariate_taylor.rs:1097-1127"""
+    T = G.TaylorPoly
+    f, g = G.taylor([[1.0, 2.0], [3.0, 4.0]]), G.taylor([[5.0, 6.0], [7.0, 8.0]])
+    assert f * g == G.taylor([[5.0, 16.0], [22.0, 60.0]])
+    assert f * T.zero() == T.zero_with([2, 2])
+    assert T.zero() * f == T.zero_with([2, 2])
+    assert f * T.one() == f
+    assert T.one() * f == f
+    assert T.from_u32(2) * f == G.taylor([[2.0, 4.0], [6.0, 8.0]])
+    assert f * T.from_u32(2) == G.taylor([[2.0, 4.0], [6.0, 8.0]])
+
+
+def test_ref_2d_mul_factor_linear(G):
+    """multivariate_taylor.rs:1130-1160"""
+    T, taylor = G.TaylorPoly, G.taylor
+    f = taylor([[1.0, 2.0], [3.0, 4.0]])
+    g0 = T.from_u32(2) * T.var_at_zero(0, 2)
+    assert g0.extract_linear() == (0.0, 2.0, 0)
+    g1 = T.from_u32(3) * T.var_at_zero(1, 2)
+    assert g1.extract_linear() == (0.0, 3.0, 1)
+    assert f * g0 == taylor([[0.0, 0.0], [2.0, 4.0]])
+    assert f * g1 == taylor([[0.0, 3.0], [0.0, 9.0]])
+    assert g0 * f == taylor([[0.0, 0.0], [2.0, 4.0]])
+    assert g1 * f == taylor([[0.0, 3.0], [0.0, 9.0]])
+    assert g0 * g1 == taylor([[0.0, 0.0], [0.0, 6.0]])
+    assert g1 * g0 == taylor([[0.0, 0.0], [0.0, 6.0]])
+    g0 = taylor([3.0, 2.0])
+    assert g0.extract_linear() == (3.0, 2.0, 0)
+    g1 = taylor([[3.0, 2.0], [0.0, 0.0]])
+    assert g1.extract_linear() == (3.0, 2.0, 1)
+    assert f * g0 == taylor([[3.0, 6.0], [11.0, 16.0]])
+    assert f * g1 == taylor([[3.0, 8.0], [9.0, 18.0]])
+    assert g0 * f == taylor([[3.0, 6.0], [11.0, 16.0]])
+    assert g1 * f == taylor([[3.0, 8.0], [9.0, 18.0]])
+    assert g0 * g1 == taylor([[9.0, 6.0], [6.0, 4.0]])
+    assert g1 * g0 == taylor([[9.0, 6.0], [6.0, 4.0]])
+
+
+def test_ref_2d_div(G):
+    """multivariate_taylor.rs:1256-1268 (general N-D divisor: wavefront kernel, tolerance)"""
+    f, g = G.taylor([[1.0, 2.0], [3.0, 4.0]]), G.taylor([[5.0, 6.0], [7.0, 8.0]])
+    r = f / g
+    ref = np.array([[0.2, 0.159_999_999_999_999_98], [0.319_999_999_999_999_95, -0.127_999_999_999_999_9]])
+    np.testing.assert_allclose(r.array(), ref, rtol=RTOL)
+    np.testing.assert_allclose((r * g).array(), f.array(), rtol=RTOL)
+
+
+def test_ref_exp(G):
+    """multivariate_taylor.rs:1389-1437 (device exp() differs from glibc by <= 1 ulp: tolerance)"""
+    T, taylor = G.TaylorPoly, G.taylor
+    assert T.zero().exp() == T.one()
+    a = T.var(0, 1.0, 5)
+    assert a.exp().extend([5, 4]) == a.extend([5, 4]).exp()
+    c = a * a * a
+    assert c.exp().extend([5, 4]) == c.extend([5, 4]).exp()
+    f, g = taylor([[1.0, 2.0], [3.0, 4.0]]), taylor([[5.0, 6.0], [7.0, 8.0]])
+    np.testing.assert_allclose(f.exp().array(), [[2.718_281_828_459_045, 5.436_563_656_918_09],
+                                                 [8.154_845_485_377_136, 27.182_818_284_590_454]], rtol=RTOL)
+    np.testing.assert_allclose((f.exp() * (-f).exp()).array(), [[1.0, 0.0], [0.0, 0.0]], rtol=RTOL, atol=1e-14)
+    np.testing.assert_allclose((f + g).exp().array(), [[403.428_793_492_735_1, 3_227.430_347_941_881],
+                                                       [4_034.287_934_927_351, 37_115.449_001_331_63]], rtol=RTOL)
+    np.testing.assert_allclose((f.exp() * g.exp()).array(), (f + g).exp().array(), rtol=RTOL)
+
+
+def test_ref_log(G):
+    """multivariate_taylor.rs:1440-1513"""
+    T, taylor = G.TaylorPoly, G.taylor
+    assert T.one().log() == T.zero()
+    xp1 = T.var(0, 1.0, 5)
+    assert xp1.log() == taylor([0.0, 1.0, -0.5, 0.333_333_333_333_333_3, -0.25])
+    e = taylor([1.0, 2.0, 3.0])
+    assert e.log() == taylor([0.0, 2.0, 1.0])
+    assert e.log().exp() == e
+    a = T.var(0, 1.0, 5)
+    assert a.log().extend([5, 4]) == a.extend([5, 4]).log()
+    f = taylor([[1.0, 2.0, 3.0], [4.0, 5.0, 6.0], [7.0, 8.0, 9.0]])
+    g = taylor([[5.0, 6.0, 7.0], [7.0, 8.0, 9.0], [9.0, 10.0, 11.0]])
+    np.testing.assert_allclose(f.log().array(), [[0.0, 2.0, 1.0], [4.0, -3.0, 0.0], [-1.0, 6.0, -4.5]], rtol=RTOL, atol=1e-13)
+    np.testing.assert_allclose(f.log().exp().array(), f.array(), rtol=RTOL)
+    np.testing.assert_allclose(f.exp().log().array(), f.array(), rtol=1e-11)
+    np.testing.assert_allclose((f * g).log().array(), (f.log() + g.log()).array(), rtol=1e-11, atol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------
+# seeded random parity against the oracle, every operator
+# ---------------------------------------------------------------------------------------------
+SHAPES = [((5,), (5,)), ((3, 4), (6, 5)), ((4, 1, 3), (4, 2, 5)), ((2, 3, 2, 3), (3, 3, 3, 3)), ((7, 6), (7, 6))]
+
+
+def rand(rng, shape, positive=False):
+    a = rng.uniform(0.5, 1.5, shape) if positive else rng.standard_normal(shape)
+    return a
+
+
+@pytest.mark.parametrize("sa,da", SHAPES)
+@pytest.mark.parametrize("sb,db", SHAPES)
+def test_binary_ops_match_oracle(G, sa, da, sb, db):
+    rng = np.random.default_rng(hash((sa, sb)) % 2**32)
+    a, b = rand(rng, sa), rand(rng, sb, positive=True)
+    ga, oa = both(G, a, da)
+    gb, ob = both(G, b, db)
+    assert_same(ga + gb, oa + ob)
+    assert_same(ga - gb, oa - ob)
+    assert_same(gb - ga, ob - oa)
+    assert_same(ga * gb, oa * ob)  # reference-order kernel: bit-exact
+    assert_close(ga / gb, oa / ob, rtol=1e-10)  # general divisor: conditioning of the recurrence
+    assert_same(-ga, -oa)
+
+
+def test_scalar_fast_paths(G):
+    """Add/Sub scalar paths (:862-869, :919-926) incl. signed zeros; Mul/Div by constants."""
+    a = np.array([[1.5, -0.0, 2.0], [0.0, -3.0, 4.0]])
+    ga, oa = both(G, a, (4, 5))
+    for s in (0.0, 2.5, -1.0, 1.0):
+        gs, os_ = G.TaylorPoly.from_scalar(s), O().TaylorPoly.from_scalar(s)
+        assert_same(ga + gs, oa + os_)
+        assert_same(gs + ga, os_ + oa)
+        assert_same(ga - gs, oa - os_)
+        assert_same(gs - ga, os_ - oa)
+        assert_same(ga * gs, oa * os_)
+        assert_same(gs * ga, os_ * oa)
+        if s != 0.0:
+            assert_same(ga / gs, oa / os_)
+
+
+@pytest.mark.parametrize("shape,deg", [((6,), (8,)), ((4, 5), (6, 5)), ((3, 4, 5), (3, 6, 5)), ((2, 2, 3, 4), (4, 4, 4, 4))])
+def test_gathers_match_oracle(G, shape, deg):
+    rng = np.random.default_rng(1234)
+    a = rand(rng, shape)
+    g, o = both(G, a, deg)
+    for v in range(len(shape)):
+        for n in range(0, deg[v]):
+            assert_same(g.derivative(v, n), o.derivative(v, n))
+            assert_same(g.taylor_expansion_of_coeff(v, n), o.taylor_expansion_of_coeff(v, n))
+            assert_same(g.shift_down(v, n), o.shift_down(v, n))
+            assert_same(g.coefficients_of_term(v, n), o.coefficients_of_term(v, n))
+            assert_same(g.taylor_polynomial(v, n), o.taylor_polynomial(v, n))
+        assert_same(g.taylor_polynomial_terms(v, [0, 2]), o.taylor_polynomial_terms(v, [0, 2]))
+        assert_same(g.taylor_polynomial_terms(v, [1]), o.taylor_polynomial_terms(v, [1]))
+    assert_same(g.truncate_to_degree_p1(3), o.truncate_to_degree_p1(3))
+    assert_same(g.truncate_to_degree_p1(2), o.truncate_to_degree_p1(2))
+    assert_same(g.remove_last_variable(), o.remove_last_variable())
+    assert_same(g.extend_to_dim(len(shape) + 2, 7), o.extend_to_dim(len(shape) + 2, 7))
+    # beyond-ndim variable conventions (:343-348, :460-465)
+    assert_same(g.coefficients_of_term(len(shape) + 1, 0), o.coefficients_of_term(len(shape) + 1, 0))
+    assert_same(g.coefficients_of_term(len(shape) + 1, 1), o.coefficients_of_term(len(shape) + 1, 1))
+
+
+def test_shift_down_long_lanes(G):
+    """shift_down along the last axis uses ndarray's 8-way unrolled fold order (restated in the oracle)."""
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal((5, 37))
+    g, o = both(G, a)
+    for n in (1, 7, 8, 9, 20, 35, 36):
+        assert_same(g.shift_down(1, n), o.shift_down(1, n))
+        assert_same(g.shift_down(0, min(n, 4)), o.shift_down(0, min(n, 4)))
+
+
+def test_readers_and_panics(G):
+    a = np.arange(12, dtype=np.float64).reshape(3, 4) + 1
+    g, o = both(G, a, (5, 6))
+    assert g.constant_term() == o.constant_term() == 1.0
+    assert g.coefficient([2, 3]) == o.coefficient([2, 3]) == 12.0
+    assert g.coefficient([4, 5]) == o.coefficient([4, 5]) == 0.0
+    with pytest.raises(G.TaylorPanic):
+        g.coefficient([5, 0])  # index >= degrees_p1 -> the reference asserts (:318-322)
+    with pytest.raises(G.TaylorPanic):
+        g.derivative(0, 5)     # n >= len_of(v) (:459)
+    with pytest.raises(G.TaylorPanic):
+        g.shift_down(2, 0)     # v >= num_vars (:516)
+    np.testing.assert_array_equal(g.gather_axis(0, 5), [1.0, 5.0, 9.0, 0.0, 0.0])
+    np.testing.assert_array_equal(g.gather_axis(1, 6), [1.0, 2.0, 3.0, 4.0, 0.0, 0.0])
+    assert g.evaluate_all_one() == o.evaluate_all_one() == 78.0
+    assert g.extract_constant() is None and G.TaylorPoly.from_scalar(3.0).extract_constant() == 3.0
+    assert not g.is_zero() and G.TaylorPoly.zero().is_zero() and G.TaylorPoly.one().is_one()
+
+
+def test_extract_linear_matches_oracle(G):
+    cases = [np.array([3.0, 2.0]), np.array([[3.0, 2.0], [0.0, 0.0]]), np.array([[3.0, 0.0], [2.0, 0.0]]),
+             np.array([[3.0, 2.0], [1.0, 0.0]]), np.array([[0.0, 0.0], [0.0, 0.0]]), np.array([1.0, 2.0, 3.0]),
+             np.array([1.0, 2.0, 0.0]), np.zeros((2, 3, 2)), np.array([[[1.0, 0.0]], [[5.0, 0.0]]])]
+    for a in cases:
+        g, o = both(G, a)
+        assert g.extract_linear() == o.extract_linear(), a
+
+
+@pytest.mark.parametrize("shape,deg", [((4,), (9,)), ((3, 3), (5, 4)), ((2, 3, 2), (4, 4, 3)), ((1, 4), (3, 6))])
+def test_exp_log_pow_match_oracle(G, shape, deg):
+    rng = np.random.default_rng(99)
+    a = rng.uniform(0.5, 1.5, shape)
+    g, o = both(G, a, deg)
+    assert_close(g.exp(), o.exp(), rtol=1e-12)
+    assert_close(g.log(), o.log(), rtol=1e-11)
+    for e in (0, 1, 2, 5):
+        assert_close(g.pow(e), o.pow(e), rtol=1e-12)
+
+
+@pytest.mark.parametrize("n,deg", [(1, 12), (2, 7), (3, 5)])
+def test_subst_var_matches_oracle(G, n, deg):
+    rng = np.random.default_rng(7 + n)
+    a = rng.uniform(0.1, 1.0, (deg,) * n)
+    s = rng.uniform(0.1, 1.0, (deg,) * n)
+    g, o = both(G, a)
+    gs, os_ = both(G, s)
+    for v in range(n):
+        assert_same(g.subst_var(v, gs), o.subst_var(v, os_))             # Horner of ordered products: bit-exact
+        lin_g, lin_o = G.TaylorPoly.from_scalar(0.3) * G.TaylorPoly.var_at_zero(v, deg), \
+            O().TaylorPoly.from_scalar(0.3) * O().TaylorPoly.var_at_zero(v, deg)
+        assert_same(g.subst_var(v, lin_g), o.subst_var(v, lin_o))        # m^i scaling path (:555-568)
+        assert_same(g.subst_var(v, G.TaylorPoly.zero()), o.subst_var(v, O().TaylorPoly.zero()))
+
+
+@pytest.mark.parametrize("shape,ylen,axis", [((40,), 3, 0), ((300,), 2, 0), ((6, 9), 4, 1), ((9, 6), 5, 0),
+                                              ((3, 8, 4), 3, 1), ((70000, 5), 2, 1)])
+def test_div_single_axis_bit_exact(G, shape, ylen, axis):
+    """p / (1 - q v)-style divisors (semantics/gf.rs:465-519): single-axis recurrence, bit-exact."""
+    rng = np.random.default_rng(31)
+    x = rng.uniform(0.0, 1.0, shape)
+    yshape = [1] * len(shape)
+    yshape[axis] = ylen
+    y = rng.uniform(0.2, 1.0, yshape)
+    deg = list(shape)
+    deg[axis] += 3  # the quotient is longer than the numerator along the divisor's axis
+    gx, ox = both(G, x, deg)
+    gy, oy = both(G, y, deg)
+    assert_same(gx / gy, ox / oy)
+
+
+# ---------------------------------------------------------------------------------------------
+# univariate TaylorExpansion (src/univariate_taylor.rs tests :119-148, :480-578)
+# ---------------------------------------------------------------------------------------------
+def test_univariate_reference_tests(G):
+    E = G.TaylorExpansion
+    x = E.var(2.0, 4)
+    g = (x * x + E.one()).exp().taylor_expansion_of_coeff(2)
+    np.testing.assert_allclose(g.coeffs(), [1_335.718_431_923_189_4, 6_530.179_000_513_37, 17_067.513_296_796_307], rtol=RTOL)
+    x, y = E.var(1.0, 2), E.var(2.0, 2)
+    assert x.subst(y) == E.from_coefficients([3.0, 1.0, 0.0])
+    assert (x * x).subst(y * y) == E.from_coefficients([25.0, 40.0, 26.0])
+    x = E.var(0.0, 9)
+    assert x / (x - E.one()) == E.from_coefficients([0.0] + [-1.0] * 9)
+    assert E.one() / (x - E.one()) == E.from_coefficients([-1.0] * 10)
+    np.testing.assert_allclose((E.one() / x.exp()).coeffs(),
+                               [1.0, -1.0, 0.5, -0.166_666_666_666_666_63, 0.041_666_666_666_666_63,
+                                -0.008_333_333_333_333_31, 0.001_388_888_888_888_877, -0.000_198_412_698_412_693_37,
+                                0.000_024_801_587_301_585_587, -2.755_731_922_398_079_3e-6], rtol=1e-12)
+    x = E.var(1.0, 4)
+    assert x.log() == E.from_coefficients([0.0, 1.0, -0.5, 0.333_333_333_333_333_3, -0.25])
+    e = E.from_coefficients([1.0, 2.0, 3.0])
+    assert e.log() == E.from_coefficients([0.0, 2.0, 1.0])
+    assert e.log().exp() == e
+
+
+@pytest.mark.parametrize("n", [1, 5, 64, 300, 1000])
+def test_univariate_matches_oracle(G, n):
+    rng = np.random.default_rng(n)
+    a, b = rng.uniform(0.5, 1.5, n), rng.uniform(0.5, 1.5, n)
+    E, OE = G.TaylorExpansion, O().TaylorExpansion
+    ga, gb, oa, ob = E.from_coefficients(a), E.from_coefficients(b), OE.from_coefficients(a), OE.from_coefficients(b)
+    gc, oc = E.constant(1.25), OE.constant(1.25)
+    same = lambda g, o: np.testing.assert_array_equal(g.coeffs().view(np.uint64), o.coeffs().view(np.uint64))
+    for f in (lambda x, y: x + y, lambda x, y: x - y, lambda x, y: x * y, lambda x, y: x / y):
+        same(f(ga, gb), f(oa, ob))
+        same(f(ga, gc), f(oa, oc))
+        same(f(gc, ga), f(oc, oa))
+        same(f(gc, gc), f(oc, oc))
+    same(-ga, -oa)
+    same(ga.pow(3), oa.pow(3))
+    np.testing.assert_allclose(ga.exp().coeffs(), oa.exp().coeffs(), rtol=1e-12)
+    np.testing.assert_allclose(ga.log().coeffs(), oa.log().coeffs(), rtol=1e-10, atol=1e-13)
+    assert ga.coeff(n - 1) == oa.coeff(n - 1)
+    assert ga.derivative(min(n - 1, 5)) == oa.derivative(min(n - 1, 5))
+    same(ga.taylor_expansion_of_coeff(n // 2), oa.taylor_expansion_of_coeff(n // 2))
