@@ -86,6 +86,7 @@ struct Ctx {
   u64 gather_cap = 0;
   u64 launches = 0;
   bool fast_mul = true;
+  std::shared_ptr<void> fast_plans;  // per-context cache of product plans (kernels_mul_fast.cu)
 
   BufP alloc(u64 n_doubles);
   void sync() { GTP_CUDA(cudaStreamSynchronize(stream)); }
