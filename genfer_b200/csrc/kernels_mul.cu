@@ -180,6 +180,7 @@ void launch_mul(Ctx& ctx, const MulArgs& a) {
 __global__ void __launch_bounds__(256) k_probe_dfma(int iters, double seed, double* sink) {
   double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
   const double m = 1.0000001, c = 1e-9;
+#pragma unroll 8
   for (int i = 0; i < iters; i++) {
     a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
     a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
@@ -200,16 +201,81 @@ __global__ void __launch_bounds__(256) k_probe_dmma(int iters, double seed, doub
   if (s == 12345.678) sink[0] = s;
 }
 
+// kind 2/4: the register row-convolution pattern of the tiled kernel (z[k] += x[j]*y[k-j], 136 DFMA,
+//           operands resident in registers, nothing else in the loop) at 16 / 8 warps per SM
+// kind 3/5: the 2x2-blocked pattern (544 DFMA into 3 accumulator rows) at 8 / 12 warps per SM
+// They bound what ANY schedule of this arithmetic can reach on the FP64 pipe (register-file operand
+// bandwidth included), separately from shared-memory and control overheads.
+__global__ void __launch_bounds__(128) k_probe_rowconv(int iters, const double* __restrict__ src, double* sink) {
+  extern __shared__ double dummy_smem[];
+  double x[16], y[16], z[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    x[i] = src[(threadIdx.x + i) & 63];
+    y[i] = src[(threadIdx.x + 2 * i + 1) & 63];
+    z[i] = 0.0;
+  }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int j = 0; j < 16; j++)
+#pragma unroll
+      for (int k = j; k < 16; k++) z[k] = fma(x[j], y[k - j], z[k]);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) s += z[i];
+  if (s == 12345.678) sink[0] = s + dummy_smem[0];
+}
+__global__ void __launch_bounds__(128) k_probe_block22(int iters, const double* __restrict__ src, double* sink) {
+  extern __shared__ double dummy_smem[];
+  double xa[16], xb[16], y0[16], y1[16], z0[16], z1[16], z2[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    xa[i] = src[(threadIdx.x + i) & 63];
+    xb[i] = src[(threadIdx.x + 3 * i + 2) & 63];
+    y0[i] = src[(threadIdx.x + 2 * i + 1) & 63];
+    y1[i] = src[(threadIdx.x + 5 * i + 3) & 63];
+    z0[i] = z1[i] = z2[i] = 0.0;
+  }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int j = 0; j < 16; j++)
+#pragma unroll
+      for (int k = j; k < 16; k++) {
+        z0[k] = fma(xa[j], y0[k - j], z0[k]);
+        z1[k] = fma(xa[j], y1[k - j], z1[k]);
+        z1[k] = fma(xb[j], y0[k - j], z1[k]);
+        z2[k] = fma(xb[j], y1[k - j], z2[k]);
+      }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) s += z0[i] + z1[i] + z2[i];
+  if (s == 12345.678) sink[0] = s + dummy_smem[0];
+}
+
 void fp64_peak_probe(Ctx& ctx, int kind, int iters, double* flops, double* ms) {
-  BufP sink = ctx.alloc(1);
+  BufP sink = ctx.alloc(64);
+  GTP_CUDA(cudaMemsetAsync(sink->d, 0, 64 * sizeof(double), ctx.stream));
   int grid = ctx.sm_count * 8, block = 256;
+  size_t smem = 0;
+  if (kind >= 2) {
+    block = 128;
+    int ctas_per_sm = (kind == 2) ? 4 : (kind == 5 ? 3 : 2);
+    smem = (size_t)(220 * 1024 / ctas_per_sm) & ~(size_t)1023;  // dynamic smem only to pin the occupancy
+    grid = ctx.sm_count * ctas_per_sm;
+    GTP_CUDA(cudaFuncSetAttribute(k_probe_rowconv, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+    GTP_CUDA(cudaFuncSetAttribute(k_probe_block22, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+  }
   cudaEvent_t e0, e1;
   GTP_CUDA(cudaEventCreate(&e0));
   GTP_CUDA(cudaEventCreate(&e1));
   for (int rep = 0; rep < 2; rep++) {  // first pass warms up
     GTP_CUDA(cudaEventRecord(e0, ctx.stream));
     if (kind == 0) GTP_LAUNCH(ctx, k_probe_dfma, grid, block, 0, iters, 1.0, sink->d);
-    else GTP_LAUNCH(ctx, k_probe_dmma, grid, block, 0, iters, 1.0, sink->d);
+    else if (kind == 1) GTP_LAUNCH(ctx, k_probe_dmma, grid, block, 0, iters, 1.0, sink->d);
+    else if (kind == 2 || kind == 4) GTP_LAUNCH(ctx, k_probe_rowconv, grid, block, smem, iters, sink->d, sink->d);
+    else GTP_LAUNCH(ctx, k_probe_block22, grid, block, smem, iters, sink->d, sink->d);
     GTP_CUDA(cudaEventRecord(e1, ctx.stream));
     GTP_CUDA(cudaEventSynchronize(e1));
   }
@@ -218,8 +284,11 @@ void fp64_peak_probe(Ctx& ctx, int kind, int iters, double* flops, double* ms) {
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   double threads = (double)grid * block;
-  double f = (kind == 0) ? threads * (double)iters * 8.0 * 2.0
-                         : (threads / 32.0) * (double)iters * 4.0 * (8.0 * 8.0 * 4.0) * 2.0;
+  double f;
+  if (kind == 0) f = threads * (double)iters * 8.0 * 2.0;
+  else if (kind == 1) f = (threads / 32.0) * (double)iters * 4.0 * (8.0 * 8.0 * 4.0) * 2.0;
+  else if (kind == 2 || kind == 4) f = threads * (double)iters * 136.0 * 2.0;
+  else f = threads * (double)iters * 544.0 * 2.0;
   *ms = t;
   *flops = f / (t * 1e-3);
 }
