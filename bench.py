@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""bench.py -- truncated N-D Taylor product FP64 GFLOP/s (BASELINE.json's metric) on synthetic dense cubes.
+
+A *step* is one full truncated product Z = X (*) Y of two dense D^n coefficient tensors
+(general path, multivariate_taylor.rs:984-1012); default workload = 6 variables x degree 15
+(16^6 = 16.8 M coefficients, 128 MiB per tensor, 1.2655e13 algorithmic FLOP), the largest
+single-GPU point of BASELINE.json's synthetic sweep.
+
+  python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--workload 6x16]
+
+N > 1 (launched by torch.distributed.run, one rank per GPU): the SAME product, output rows sharded
+over the ranks with the folded-cyclic map of genfer_b200/partition.py; Y lives block-sharded and is
+replicated by one NCCL all-gather inside every timed step ("strong" scaling: total work fixed).
+
+Numbers reported (one JSON line, rank 0):
+  value     whole-job GFLOP/s, operands resident in HBM, CUDA events, max over ranks
+  e2e       same metric through the reference-facing operator (gtp_from_host x2 -> gtp_mul -> gtp_to_host
+            at N=1; pinned H2D -> PartitionedProduct -> D2H at N>1) with host buffers
+  roofline  product kernel vs the FP64 FMA pipe peak measured live by the library's DFMA probe
+  cpu_baseline  the CPU oracle (reference loop order, 1 thread -- the reference is single-threaded)
+            on a bounded sample of the same workload, rank 0 at N=1 only
+`--impl reference` times that oracle alone (the reference is Rust; no cargo in this image).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "truncated N-D Taylor product FP64 GFLOP/s"
+UNIT = "GFLOP/s"
+
+
+def parse_workload(w: str):
+    n, d = (int(t) for t in w.lower().split("x"))
+    return n, d
+
+
+def workload_name(n: int, d: int) -> str:
+    return f"synthetic TaylorPoly product, {n} vars x degree {d - 1} ({d}^{n} = {d ** n} coefficients per tensor)"
+
+
+def synth_inputs(n: int, d: int):
+    from genfer_b200.synth import SEED_X, SEED_Y, synth_uniform
+    shape = (d,) * n
+    return synth_uniform(shape, SEED_X), synth_uniform(shape, SEED_Y)
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU sample: output rows Z[0, k1, ...] for k1 in `k1s` -- the same loop nest one level down
+# (row k0 = 0 of the product only involves X[0], Y[0]), executed by the oracle in reference order.
+# ---------------------------------------------------------------------------------------------
+def cpu_sample_rows(n: int, d: int, budget_macs: float):
+    per_sub = (d * (d + 1) // 2) ** (n - 2)          # MACs of one (n-2)-D sub-product
+    k1s, macs = [], 0.0
+    for k1 in range(d - 1, -1, -1):                     # heaviest rows first
+        if macs + (k1 + 1) * per_sub > budget_macs and k1s:
+            break
+        k1s.append(k1)
+        macs += (k1 + 1) * per_sub
+    return sorted(k1s), macs
+
+
+def run_cpu_sample(x: np.ndarray, y: np.ndarray, k1s):
+    """Returns (rows result dict, MACs, seconds).  x, y are the full tensors; only X[0], Y[0] are touched."""
+    from oracle import oracle as O
+    O.build()
+    x0, y0 = np.ascontiguousarray(x[0]), np.ascontiguousarray(y[0])
+    t0 = time.perf_counter()
+    r, macs = O.mul_rows(x0, y0, x0.shape, k1s)
+    dt = time.perf_counter() - t0
+    return r, macs, dt
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._pump, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.perf_counter(), ln.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], None, set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, ln in self.lines:
+            f = [c.strip() for c in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                clk, mx = float(f[1]), float(f[2])
+            except ValueError:
+                continue
+            smax = mx
+            if t0 <= t <= t1 + 0.1:
+                sm.append(clk)
+                try:
+                    power.append(float(f[3]))
+                except ValueError:
+                    pass
+                for nm, v in zip(names, f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        if not sm:  # region shorter than one sample: take the nearest ones
+            sm = [float(ln.split(",")[1]) for _, ln in self.lines[-3:] if len(ln.split(",")) >= 9] or [0.0]
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+# ---------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference's own CPU implementation of the path.  The reference is Rust and cannot be built in this
+    image (no cargo/rustc), so this is the oracle port: same loop order, separate multiply and add, 1 thread
+    (the reference is single-threaded: src/main.rs:96-106, every IR node is an Rc)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n, d = parse_workload(args.workload)
+    x, y = synth_inputs(n, d)
+    k1s, _ = cpu_sample_rows(n, d, budget_macs=args.cpu_budget_gmac * 1e9 * 0.4)
+    times, macs = [], 0.0
+    for i in range(args.warmup + args.steps):
+        _, macs, dt = run_cpu_sample(x, y, k1s)
+        if i >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = 2.0 * macs * len(times) / total / 1e9
+    sample = (f"output rows Z[0, k1, ...], k1 in {k1s[0]}..{k1s[-1]} of the {workload_name(n, d)}: "
+              f"{macs:.4g} MACs per step (of {full_macs(n, d):.4g}), oracle port in reference loop order, "
+              f"g++ -O2 -ffp-contract=off")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(n, d), "inputs": "iid uniform [0,1), splitmix64 seeds 20230517/20231210"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                             "host_cores": host_cores()},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def full_macs(n: int, d: int) -> float:
+    return float((d * (d + 1) // 2) ** n)
+
+
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import genfer_b200
+    from genfer_b200.partition import PartitionedProduct, gpu_row_kernel, rows_for_rank, shard_bounds
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the f64 Taylor path has no CPU fallback "
+                         "(use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n, d = parse_workload(args.workload)
+    shape = (d,) * n
+    K, W = args.steps, args.warmup
+    flops = 2.0 * full_macs(n, d)
+
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx = genfer_b200.Context(local, stream=stream.cuda_stream)
+    kind = ctx.mul_kernel_kind(shape, shape, shape)
+
+    xh_np, yh_np = synth_inputs(n, d)
+    hx = torch.from_numpy(xh_np).pin_memory()
+    hy = torch.from_numpy(yh_np).pin_memory()
+    dx = hx.to("cuda", non_blocking=True)
+    dy = hy.to("cuda", non_blocking=True)
+    pp = PartitionedProduct(shape, shape, shape, gpu_row_kernel(ctx))
+    y_shard = pp.shard_of(dy) if world > 1 else dy
+    lo, hi, block = shard_bounds(d, world, rank)
+    hy_shard = torch.zeros((block,) + shape[1:], dtype=torch.float64).pin_memory()
+    hy_shard[: hi - lo] = hy[lo:hi]
+    out_rows = torch.empty((len(pp.rows),) + shape[1:], dtype=torch.float64, device="cuda")
+    h_out = torch.empty((len(pp.rows),) + shape[1:], dtype=torch.float64).pin_memory()
+    row_kernel = gpu_row_kernel(ctx)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+
+    def step(i=None):
+        y_full = pp.gather_operand(y_shard, d)            # NCCL all-gather (no-op at N=1)
+        if i is not None:
+            kev[i][0].record()
+        row_kernel(shape, dx, shape, y_full, shape, pp.rows, out_rows)
+        if i is not None:
+            kev[i][1].record()
+
+    # ---- device-resident timing ------------------------------------------------------------
+    for _ in range(W):
+        step()
+    torch.cuda.synchronize()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    barrier()
+    torch.cuda.synchronize()
+    l0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_host0 = time.perf_counter()
+    e0.record()
+    for i in range(K):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    t_host1 = time.perf_counter()
+    launches = ctx.launch_count - l0
+    clocks = sampler.stop(t_host0, t_host1) if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    ms_kernel = sum(a.elapsed_time(b) for a, b in kev) / K
+    t = torch.tensor([ms_total, ms_kernel], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_kernel_max = float(t[0]), float(t[1])
+    value = flops * K / (ms_total * 1e-3) / 1e9
+
+    # ---- end to end with host buffers ----------------------------------------------------------
+    def e2e_step():
+        if world == 1:   # the reference-facing operator surface through the C ABI
+            X = genfer_b200.TaylorPoly.from_host_ptr(hx.data_ptr(), shape, shape, ctx)
+            Y = genfer_b200.TaylorPoly.from_host_ptr(hy.data_ptr(), shape, shape, ctx)
+            Z = X * Y
+            Z.to_host_ptr(h_out.data_ptr())               # synchronises
+        else:
+            dx.copy_(hx, non_blocking=True)
+            y_shard.copy_(hy_shard, non_blocking=True)
+            step()
+            h_out.copy_(out_rows, non_blocking=True)
+            torch.cuda.synchronize()
+
+    for _ in range(min(W, 2)):
+        e2e_step()
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        e2e_step()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    te = torch.tensor([t1 - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = flops * K / float(te[0]) / 1e9
+    h2d = hx.numel() * 8 + (hy.numel() * 8 if world == 1 else hy_shard.numel() * 8)
+    d2h = h_out.numel() * 8
+    e2e_out_sample = h_out[0, :].clone() if rank == 0 else None   # Z[0, ...] (row 0 belongs to rank 0)
+
+    # ---- roofline of the product kernel ---------------------------------------------------------
+    my_rows_macs = sum(k + 1 for k in pp.rows) * float((d * (d + 1) // 2) ** (n - 1))
+    achieved = 2.0 * my_rows_macs / (ms_kernel * 1e-3) / 1e12           # this rank's launch
+    peak_fl, _ = ctx.fp64_peak_probe(0, 16384)
+    peak = peak_fl / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "product_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(args.workload, {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "fp64", "kernel": "k_mul_tiled22" if kind == 1 and d == 16 else ("k_mul_tiled" if kind == 1 else "k_mul_ordered"),
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": traffic,
+                "peak_source": "FP64 FMA pipe measured live by gtp_fp64_peak_probe (8 independent DFMA chains/thread, all SMs); "
+                               "MEASURED_PEAKS.json has no FP64 entry; DMMA m8n8k4 measures the same rate (profiles/fp64_peaks.json)",
+                "algorithmic_flop_per_launch": 2.0 * my_rows_macs, "kernel_ms": ms_kernel}
+
+    # ---- HBM-bound axis reduction on the same tensors (Metric 1b, shift_down) ---------------------
+    aux = []
+    if world == 1 and not args.no_aux:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        hbm_peak = json.load(open(peaks_path))["hbm_gbs"] if os.path.exists(peaks_path) else 6650.0
+        hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if os.path.exists(peaks_path) else "6.65 TB/s (of fallback)"
+        TX = genfer_b200.TaylorPoly.from_device(dx.data_ptr(), shape, shape, ctx)
+        TY = genfer_b200.TaylorPoly.from_device(dy.data_ptr(), shape, shape, ctx)
+        for v, nm in ((n - 1, "last axis"), (0, "first axis")):
+            for _ in range(3):
+                TX.shift_down(v, d - 1), TY.shift_down(v, d - 1)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 10
+            a.record()
+            for i in range(reps):                           # alternate X / Y (each 128 MiB > L2) so reads come from HBM
+                (TX if i % 2 == 0 else TY).shift_down(v, d - 1)
+            b.record()
+            torch.cuda.synchronize()
+            msr = a.elapsed_time(b) / reps
+            nbytes = 8.0 * (d ** n + d ** (n - 1))
+            aux.append({"kernel": f"shift_down({nm}, n={d - 1}): full axis reduction", "bound": "hbm",
+                        "achieved": nbytes / (msr * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": nbytes / (msr * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": nbytes,
+                        "ms": msr, "peak_source": hbm_src})
+
+    # ---- CPU baseline + parity on the sample (rank 0, N = 1) ---------------------------------------
+    cpu = None
+    parity = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        k1s, _ = cpu_sample_rows(n, d, budget_macs=args.cpu_budget_gmac * 1e9)
+        r, macs, dt = run_cpu_sample(xh_np, yh_np, k1s)
+        cpu = {"value": 2.0 * macs / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"output rows Z[0, k1, ...], k1 in {k1s[0]}..{k1s[-1]} of the same product: {macs:.4g} MACs "
+                         f"in {dt:.1f} s; oracle port, reference loop order, 1 thread (the reference is single-threaded)",
+               "host_cores": host_cores(), "seconds": dt}
+        got = e2e_out_sample.numpy()[k1s]
+        ref = r[k1s]
+        parity = {"vs": "oracle, same inputs, rows Z[0, k1, ...] of the e2e result",
+                  "max_rel_err": float(np.max(np.abs(got - ref) / np.abs(ref))), "tolerance": 1e-12,
+                  "coefficients_checked": int(ref.size)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(n, d),
+                           "inputs": "iid uniform [0,1), splitmix64 seeds 20230517/20231210; X, Y, Z = "
+                                     f"{3 * d ** n * 8 / 2 ** 20:.0f} MiB" + (" > 126 MB L2 (inputs larger than L2)" if 3 * d ** n * 8 > 126e6 else
+                                                                               " (fits L2; compute-bound kernel, arithmetic intensity > 1 kFLOP/B)"),
+                           "parallelism": "1 GPU" if world == 1 else
+                           f"output rows folded-cyclic over {world} GPUs, Y block-sharded + NCCL all-gather per step",
+                           "kernel": roofline["kernel"]},
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "api": "gtp_from_host x2 -> gtp_mul -> gtp_to_host" if world == 1 else
+                               "pinned H2D (X, Y shard) -> all-gather -> gtp_mul_rowlist_raw -> D2H of the rank's rows"},
+                "gpu_launches": int(launches),
+                "roofline": roofline, "aux_rooflines": aux, "cpu_baseline": cpu, "parity": parity,
+                "kernel_ms_max_over_ranks": ms_kernel_max}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="6x16", help="NxD: N variables, cube edge D (degree D-1)")
+    ap.add_argument("--cpu-budget-gmac", type=float, default=40.0, help="size of the CPU sample in GMAC")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-aux", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -75,6 +75,7 @@ _SIGS = {
     "gtp_evaluate_all_one": (C.c_int, [vp, vp, f64p]),
     "gtp_eq": (C.c_int, [vp, vp, vp, intp]),
     "gtp_mul_rows_raw": (C.c_int, [vp, C.c_int, u64p, vp, u64p, vp, u64p, C.c_uint64, C.c_uint64, C.c_uint64, vp]),
+    "gtp_mul_rowlist_raw": (C.c_int, [vp, C.c_int, u64p, vp, u64p, vp, u64p, u64p, C.c_uint64, vp]),
     "gtp_mul_macs": (C.c_double, [C.c_int, u64p, u64p, u64p]),
     "gtp_mul_kernel_kind": (C.c_int, [vp, C.c_int, u64p, u64p, u64p]),
     "gtp_fp64_peak_probe": (C.c_int, [vp, C.c_int, C.c_int, f64p, f64p]),

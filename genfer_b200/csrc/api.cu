@@ -1004,6 +1004,25 @@ int gtp_mul_rows_raw(gtp_ctx* c, int ndim, const uint64_t* xshape, const double*
     launch_mul(*c, m);
   });
 }
+int gtp_mul_rowlist_raw(gtp_ctx* c, int ndim, const uint64_t* xshape, const double* x, const uint64_t* yshape, const double* y,
+                        const uint64_t* rshape, const uint64_t* rows, uint64_t n_rows, double* out_rows) {
+  return wrap(c, [&] {
+    GTP_CHECK(ndim >= 1 && ndim <= GTP_MAX_NDIM && x && y && out_rows && (rows || n_rows == 0), GTP_ERR_ARG, "bad arguments");
+    MulArgs m;
+    m.ndim = ndim;
+    m.xs = to_shape(xshape, ndim);
+    m.ys = to_shape(yshape, ndim);
+    m.rs = to_shape(rshape, ndim);
+    if (n_rows == 0) return;
+    for (uint64_t i = 0; i < n_rows; i++)
+      GTP_CHECK(rows[i] < m.rs[0], GTP_ERR_INDEX, "row outside the result's leading axis");
+    m.x = x;
+    m.y = y;
+    m.out = out_rows;
+    m.rows.assign(rows, rows + n_rows);
+    launch_mul(*c, m);
+  });
+}
 double gtp_mul_macs(int ndim, const uint64_t* xs, const uint64_t* ys, const uint64_t* rs) {
   return mul_macs(to_shape(xs, ndim), to_shape(ys, ndim), to_shape(rs, ndim));
 }

@@ -89,6 +89,7 @@ struct MulArgs {
   const double* y;
   double* out;
   u64 row_begin = 0, row_step = 1, row_count = 0;
+  std::vector<u64> rows;  // explicit leading-axis row list (overrides begin/step/count when non-empty)
   bool accumulate = false;
   double sign = 1.0;
 };

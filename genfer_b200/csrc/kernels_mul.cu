@@ -167,9 +167,42 @@ static void launch_mul_ordered(Ctx& ctx, const MulArgs& a) {
   }
 }
 
-void launch_mul(Ctx& ctx, const MulArgs& a) {
-  if (mul_kernel_kind(ctx, a) == 1) launch_mul_fast(ctx, a);
-  else launch_mul_ordered(ctx, a);
+void launch_mul(Ctx& ctx, const MulArgs& a_in) {
+  MulArgs a = a_in;
+  if (!a.rows.empty()) {
+    a.row_count = a.rows.size();
+    a.row_begin = a.rows[0];
+    a.row_step = 1;
+  }
+  if (mul_kernel_kind(ctx, a) == 1) {
+    launch_mul_fast(ctx, a);
+    return;
+  }
+  if (a.rows.empty()) {
+    launch_mul_ordered(ctx, a);
+    return;
+  }
+  // the reference-order kernel walks arithmetic progressions: one launch per maximal run of the list
+  u64 row_elems = 1;
+  for (int i = 1; i < a.ndim; i++) row_elems *= a.rs[i];
+  size_t i = 0;
+  while (i < a.rows.size()) {
+    size_t j = i + 1;
+    u64 step = 1;
+    if (j < a.rows.size() && a.rows[j] > a.rows[i]) {
+      step = a.rows[j] - a.rows[i];
+      while (j + 1 < a.rows.size() && a.rows[j + 1] > a.rows[j] && a.rows[j + 1] - a.rows[j] == step) j++;
+      j++;
+    }
+    MulArgs seg = a;
+    seg.rows.clear();
+    seg.row_begin = a.rows[i];
+    seg.row_step = step;
+    seg.row_count = j - i;
+    seg.out = a.out + i * row_elems;
+    launch_mul_ordered(ctx, seg);
+    i = j;
+  }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -33,11 +33,10 @@ struct FastP {
   unsigned xa[F_MAXA], ya[F_MAXA], ra[F_MAXA];   // lengths along the A axes
   long long xastr[F_MAXA], yastr[F_MAXA];   // element strides of the A axes in X / Y
   unsigned rows_a0;                         // number of computed rows along A axis 0 (row subset)
-  u64 row_begin, row_step;
   unsigned x_rows, y_rows, z_rows;          // rows (of LT doubles) per X / Y / Z slab
   int nsteps;
   const unsigned* table;                    // [nsteps][FT]
-  const uint4* units;                       // {packed kA index, q0, q1, unused}
+  const uint4* units;                       // {packed kA index, q0, q1, k along A axis 0}
   const double* x;
   const double* y;
   double* out;
@@ -96,7 +95,7 @@ __global__ void __launch_bounds__(FT, 3) k_mul_tiled(const FastP p) {
         unsigned len = (a == 0) ? p.rows_a0 : p.ra[a];
         unsigned idx = rem % len;
         rem /= len;
-        k[a] = (a == 0) ? (unsigned)(p.row_begin + idx * p.row_step) : idx;
+        k[a] = (a == 0) ? unit.w : idx;
         unsigned l = (k[a] + 1 > p.ya[a]) ? k[a] + 1 - p.ya[a] : 0;
         unsigned h = (k[a] + 1 < p.xa[a]) ? k[a] + 1 : p.xa[a];
         lo[a] = l;
@@ -206,7 +205,6 @@ static bool fast_geom(const MulArgs& a, FastGeom* g) {
   if (smem > 74 * 1024) return false;             // 3 CTAs per SM
   for (int d = 0; d < nd; d++)
     if (a.xs[d] == 0 || a.ys[d] == 0 || a.rs[d] == 0) return false;
-  if (a.rs[0] == 1 && (a.row_begin != 0)) return false;
   return true;
 }
 
@@ -345,7 +343,7 @@ __global__ void __launch_bounds__(FT, 2) k_mul_tiled22(const FastP p) {
         unsigned len = (a == 0) ? p.rows_a0 : p.ra[a];
         unsigned idx = rem % len;
         rem /= len;
-        k[a] = (a == 0) ? (unsigned)(p.row_begin + idx * p.row_step) : idx;
+        k[a] = (a == 0) ? unit.w : idx;
         unsigned l = (k[a] + 1 > p.ya[a]) ? k[a] + 1 - p.ya[a] : 0;
         unsigned h = (k[a] + 1 < p.xa[a]) ? k[a] + 1 : p.xa[a];
         lo[a] = l;
@@ -514,6 +512,7 @@ void launch_mul_fast(Ctx& ctx, const MulArgs& a) {
   key.v.push_back(a.row_begin);
   key.v.push_back(a.row_step);
   key.v.push_back(a.row_count);
+  key.v.insert(key.v.end(), a.rows.begin(), a.rows.end());
   auto& cache = plan_cache(ctx);
   std::shared_ptr<FastPlan> pl;
   auto it = cache.find(key);
@@ -538,8 +537,6 @@ void launch_mul_fast(Ctx& ctx, const MulArgs& a) {
       p.yastr[d] = (long long)yst[d];
     }
     p.rows_a0 = (unsigned)a.row_count;
-    p.row_begin = a.row_begin;
-    p.row_step = a.row_step;
     p.x_rows = (unsigned)(g.xb1 * g.xb2);
     p.y_rows = (unsigned)(g.yb1 * g.yb2);
     p.z_rows = (unsigned)(g.rb1 * g.rb2);
@@ -551,9 +548,11 @@ void launch_mul_fast(Ctx& ctx, const MulArgs& a) {
     // ---- work units: (packed kA, q0, q1), split-K chunks, longest first ----
     u64 n_slabs = a.row_count;
     for (int d = 1; d < na; d++) n_slabs *= a.rs[d];
-    struct U { unsigned ka, q0, q1; };
+    struct U { unsigned ka, q0, q1, k0; };
+    auto row_of = [&](u64 idx) -> u64 { return a.rows.empty() ? a.row_begin + idx * a.row_step : a.rows[idx]; };
     std::vector<U> units;
     std::vector<u64> boxes(n_slabs);
+    std::vector<unsigned> k0s(n_slabs, 0);
     u64 total_pairs = 0;
     for (u64 s = 0; s < n_slabs; s++) {
       u64 rem = s, box = 1;
@@ -561,7 +560,8 @@ void launch_mul_fast(Ctx& ctx, const MulArgs& a) {
         u64 len = (d == 0) ? a.row_count : a.rs[d];
         u64 idx = rem % len;
         rem /= len;
-        u64 k = (d == 0) ? a.row_begin + idx * a.row_step : idx;
+        u64 k = (d == 0) ? row_of(idx) : idx;
+        if (d == 0) k0s[s] = (unsigned)k;
         u64 lo = sat_sub(k + 1, a.ys[d]), hi = std::min(k + 1, a.xs[d]);
         box *= hi > lo ? hi - lo : 0;
       }
@@ -576,12 +576,12 @@ void launch_mul_fast(Ctx& ctx, const MulArgs& a) {
       if (!box) continue;
       u64 parts = (box + chunk - 1) / chunk;
       u64 per = (box + parts - 1) / parts;
-      for (u64 q0 = 0; q0 < box; q0 += per) units.push_back({(unsigned)s, (unsigned)q0, (unsigned)std::min(box, q0 + per)});
+      for (u64 q0 = 0; q0 < box; q0 += per) units.push_back({(unsigned)s, (unsigned)q0, (unsigned)std::min(box, q0 + per), k0s[s]});
     }
     std::stable_sort(units.begin(), units.end(), [](const U& x, const U& y) { return (x.q1 - x.q0) > (y.q1 - y.q0); });
     pl->n_units = (unsigned)units.size();
     std::vector<uint4> hu(units.size());
-    for (size_t i = 0; i < units.size(); i++) hu[i] = make_uint4(units[i].ka, units[i].q0, units[i].q1, 0);
+    for (size_t i = 0; i < units.size(); i++) hu[i] = make_uint4(units[i].ka, units[i].q0, units[i].q1, units[i].k0);
     pl->table = ctx.alloc((table.size() * sizeof(unsigned) + 7) / 8 + 1);
     pl->units = ctx.alloc((hu.size() * sizeof(uint4) + 7) / 8 + 1);
     GTP_CUDA(cudaMemcpyAsync(pl->table->d, table.data(), table.size() * sizeof(unsigned), cudaMemcpyHostToDevice, ctx.stream));

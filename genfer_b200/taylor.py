@@ -80,6 +80,11 @@ class Context:
                                              C.c_void_p(y_ptr), _u64(rshape), row_begin, row_step, row_count,
                                              C.c_void_p(out_ptr)))
 
+    def mul_rowlist_raw(self, xshape, x_ptr: int, yshape, y_ptr: int, rshape, rows: Sequence[int], out_ptr: int):
+        self.check(self.lib.gtp_mul_rowlist_raw(self.h, len(rshape), _u64(xshape), C.c_void_p(x_ptr), _u64(yshape),
+                                                C.c_void_p(y_ptr), _u64(rshape), _u64(rows), len(rows),
+                                                C.c_void_p(out_ptr)))
+
     def mul_kernel_kind(self, xshape, yshape, rshape) -> int:
         return int(self.lib.gtp_mul_kernel_kind(self.h, len(rshape), _u64(xshape), _u64(yshape), _u64(rshape)))
 
@@ -137,6 +142,18 @@ class TaylorPoly:
         assert a.ndim == len(degrees_p1), "coeffs.ndim() != degrees_p1.len()"
         return cls._make(ctx, "gtp_from_host", a.ndim, _u64(a.shape), _u64(degrees_p1),
                          a.ctypes.data_as(_lib.f64p))
+
+    @classmethod
+    def from_host_ptr(cls, ptr: int, shape: Sequence[int], degrees_p1: Sequence[int],
+                      ctx: Optional[Context] = None) -> "TaylorPoly":
+        """Upload prod(shape) doubles from a host address (e.g. a pinned staging buffer) without a numpy copy."""
+        ctx = ctx or default_context()
+        return cls._make(ctx, "gtp_from_host", len(shape), _u64(shape), _u64(degrees_p1),
+                         C.cast(C.c_void_p(ptr), _lib.f64p))
+
+    def to_host_ptr(self, ptr: int) -> None:
+        """Copy the stored coefficients to a host address (synchronises)."""
+        self.ctx.check(self.ctx.lib.gtp_to_host(self.ctx.h, self._h, C.c_void_p(ptr)))
 
     @classmethod
     def from_coeffs(cls, coeffs, ctx: Optional[Context] = None) -> "TaylorPoly":

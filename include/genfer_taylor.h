@@ -138,6 +138,12 @@ int gtp_eq(gtp_ctx* ctx, const gtp_poly* a, const gtp_poly* b, int* out);
 int gtp_mul_rows_raw(gtp_ctx* ctx, int ndim, const uint64_t* xshape, const double* x,
                      const uint64_t* yshape, const double* y, const uint64_t* rshape,
                      uint64_t row_begin, uint64_t row_step, uint64_t row_count, double* out_rows);
+/* Same for an explicit list of leading-axis rows (row rows[i] lands at out_rows + i*prod(rshape[1:])):
+ * one launch for a rank's load-balanced shard, e.g. the folded-cyclic map k0 mod 2W in {r, 2W-1-r},
+ * which gives every rank the same MAC count although row k0 costs (k0+1) sub-products (:1001-1010). */
+int gtp_mul_rowlist_raw(gtp_ctx* ctx, int ndim, const uint64_t* xshape, const double* x,
+                        const uint64_t* yshape, const double* y, const uint64_t* rshape,
+                        const uint64_t* rows, uint64_t n_rows, double* out_rows);
 /* MAC count of the general product (trip counts of :975-977 and :1002-1004); FLOPs = 2*MACs. */
 double gtp_mul_macs(int ndim, const uint64_t* xshape, const uint64_t* yshape, const uint64_t* rshape);
 /* Which kernel gtp_mul_rows_raw would pick for these shapes: 0 generic, 1 register-tiled. */

@@ -1,0 +1,145 @@
+//! `extern "C"` declarations for `include/genfer_taylor.h` plus a thin safe wrapper (`DevicePoly`)
+//! with the value semantics of genfer's `TaylorPoly<F64>` (src/multivariate_taylor.rs).
+//!
+//! This crate cannot be compiled in the build image (no cargo/rustc there); it is the binding a
+//! genfer maintainer adds, see INTEGRATION.md for the patch to `multivariate_taylor.rs`.
+#![allow(non_camel_case_types)]
+use std::{ffi::CStr, os::raw::{c_char, c_int, c_void}, ptr, rc::Rc};
+
+pub const GTP_UNBOUNDED: u64 = u64::MAX; // usize::MAX on 64-bit targets
+
+#[repr(C)] pub struct gtp_ctx { _p: [u8; 0] }
+#[repr(C)] pub struct gtp_poly { _p: [u8; 0] }
+#[repr(C)] pub struct gtu_series { _p: [u8; 0] }
+
+extern "C" {
+    pub fn gtp_ctx_create(device: c_int, cuda_stream: *mut c_void, out: *mut *mut gtp_ctx) -> c_int;
+    pub fn gtp_ctx_destroy(ctx: *mut gtp_ctx);
+    pub fn gtp_last_error(ctx: *mut gtp_ctx) -> *const c_char;
+    pub fn gtp_ctx_synchronize(ctx: *mut gtp_ctx) -> c_int;
+    pub fn gtp_from_host(ctx: *mut gtp_ctx, ndim: c_int, shape: *const u64, degrees_p1: *const u64, data: *const f64, out: *mut *mut gtp_poly) -> c_int;
+    pub fn gtp_to_host(ctx: *mut gtp_ctx, p: *const gtp_poly, out: *mut f64) -> c_int;
+    pub fn gtp_clone(ctx: *mut gtp_ctx, p: *const gtp_poly, out: *mut *mut gtp_poly) -> c_int;
+    pub fn gtp_free(ctx: *mut gtp_ctx, p: *mut gtp_poly);
+    pub fn gtp_ndim(p: *const gtp_poly) -> c_int;
+    pub fn gtp_len(p: *const gtp_poly) -> u64;
+    pub fn gtp_shape(p: *const gtp_poly, out: *mut u64);
+    pub fn gtp_degrees_p1(p: *const gtp_poly, out: *mut u64);
+    pub fn gtp_from_scalar(ctx: *mut gtp_ctx, x: f64, out: *mut *mut gtp_poly) -> c_int;
+    pub fn gtp_zero_with(ctx: *mut gtp_ctx, ndim: c_int, degrees_p1: *const u64, out: *mut *mut gtp_poly) -> c_int;
+    pub fn gtp_var(ctx: *mut gtp_ctx, v: u64, x: f64, len: u64, out: *mut *mut gtp_poly) -> c_int;
+    pub fn gtp_var_at_zero(ctx: *mut gtp_ctx, v: u64, len: u64, out: *mut *mut gtp_poly) -> c_int;
+    pub fn gtp_var_with_degrees_p1(ctx: *mut gtp_ctx, v: u64, x: f64, ndim: c_int, degrees_p1: *const u64, out: *mut *mut gtp_poly) -> c_int;
+    pub fn gtp_add(ctx: *mut gtp_ctx, a: *const gtp_poly, b: *const gtp_poly, out: *mut *mut gtp_poly) -> c_int;
+    pub fn gtp_sub(ctx: *mut gtp_ctx, a: *const gtp_poly, b: *const gtp_poly, out: *mut *mut gtp_poly) -> c_int;
+    pub fn gtp_mul(ctx: *mut gtp_ctx, a: *const gtp_poly, b: *const gtp_poly, out: *mut *mut gtp_poly) -> c_int;
+    pub fn gtp_div(ctx: *mut gtp_ctx, a: *const gtp_poly, b: *const gtp_poly, out: *mut *mut gtp_poly) -> c_int;
+    pub fn gtp_neg(ctx: *mut gtp_ctx, a: *const gtp_poly, out: *mut *mut gtp_poly) -> c_int;
+    pub fn gtp_exp(ctx: *mut gtp_ctx, a: *const gtp_poly, out: *mut *mut gtp_poly) -> c_int;
+    pub fn gtp_log(ctx: *mut gtp_ctx, a: *const gtp_poly, out: *mut *mut gtp_poly) -> c_int;
+    pub fn gtp_pow(ctx: *mut gtp_ctx, a: *const gtp_poly, exp: u32, out: *mut *mut gtp_poly) -> c_int;
+    pub fn gtp_derivative(ctx: *mut gtp_ctx, a: *const gtp_poly, v: u64, n: u64, out: *mut *mut gtp_poly) -> c_int;
+    pub fn gtp_taylor_expansion_of_coeff(ctx: *mut gtp_ctx, a: *const gtp_poly, v: u64, n: u64, out: *mut *mut gtp_poly) -> c_int;
+    pub fn gtp_shift_down(ctx: *mut gtp_ctx, a: *const gtp_poly, v: u64, n: u64, out: *mut *mut gtp_poly) -> c_int;
+    pub fn gtp_coefficients_of_term(ctx: *mut gtp_ctx, a: *const gtp_poly, v: u64, order: u64, out: *mut *mut gtp_poly) -> c_int;
+    pub fn gtp_taylor_polynomial_terms(ctx: *mut gtp_ctx, a: *const gtp_poly, v: u64, orders: *const u64, n_orders: c_int, out: *mut *mut gtp_poly) -> c_int;
+    pub fn gtp_subst_var(ctx: *mut gtp_ctx, a: *const gtp_poly, v: u64, subst: *const gtp_poly, out: *mut *mut gtp_poly) -> c_int;
+    pub fn gtp_truncate_to_degree_p1(ctx: *mut gtp_ctx, a: *const gtp_poly, degree_p1: u64, out: *mut *mut gtp_poly) -> c_int;
+    pub fn gtp_remove_last_variable(ctx: *mut gtp_ctx, a: *const gtp_poly, out: *mut *mut gtp_poly) -> c_int;
+    pub fn gtp_extend_to_dim(ctx: *mut gtp_ctx, a: *const gtp_poly, ndim: u64, degree_p1: u64, out: *mut *mut gtp_poly) -> c_int;
+    pub fn gtp_constant_term(ctx: *mut gtp_ctx, a: *const gtp_poly, out: *mut f64) -> c_int;
+    pub fn gtp_coefficient(ctx: *mut gtp_ctx, a: *const gtp_poly, index: *const u64, n_index: c_int, out: *mut f64) -> c_int;
+    pub fn gtp_gather_axis(ctx: *mut gtp_ctx, a: *const gtp_poly, v: u64, count: u64, out: *mut f64) -> c_int;
+    pub fn gtp_is_zero(ctx: *mut gtp_ctx, a: *const gtp_poly, out: *mut c_int) -> c_int;
+    pub fn gtp_is_one(ctx: *mut gtp_ctx, a: *const gtp_poly, out: *mut c_int) -> c_int;
+    pub fn gtp_eq(ctx: *mut gtp_ctx, a: *const gtp_poly, b: *const gtp_poly, out: *mut c_int) -> c_int;
+    // (gtp_mul_rows_raw / gtp_mul_rowlist_raw / gtu_* omitted here: same pattern, see the header)
+}
+
+/// One CUDA device + stream; `Rc` because genfer is single threaded (`src/main.rs:96-106`).
+pub struct Context(*mut gtp_ctx);
+impl Context {
+    pub fn new(device: i32) -> Rc<Self> {
+        let mut h = ptr::null_mut();
+        let rc = unsafe { gtp_ctx_create(device, ptr::null_mut(), &mut h) };
+        assert!(rc == 0, "gtp_ctx_create failed ({rc}): no CUDA device -- there is no CPU fallback for the f64 Taylor path");
+        Rc::new(Context(h))
+    }
+    /// Non-zero status becomes a panic, preserving the reference's `assert!` behaviour.
+    fn check(&self, rc: c_int) {
+        if rc != 0 {
+            let msg = unsafe { CStr::from_ptr(gtp_last_error(self.0)) }.to_string_lossy().into_owned();
+            panic!("libgenfer_taylor error {rc}: {msg}");
+        }
+    }
+}
+impl Drop for Context { fn drop(&mut self) { unsafe { gtp_ctx_destroy(self.0) } } }
+
+/// Device-resident `TaylorPoly<F64>`; operators consume by value like the reference.
+pub struct DevicePoly { ctx: Rc<Context>, h: *mut gtp_poly }
+impl Drop for DevicePoly { fn drop(&mut self) { unsafe { gtp_free(self.ctx.0, self.h) } } }
+impl Clone for DevicePoly {
+    fn clone(&self) -> Self {
+        let mut h = ptr::null_mut();
+        self.ctx.check(unsafe { gtp_clone(self.ctx.0, self.h, &mut h) }); // O(1): buffers are immutable + ref-counted
+        DevicePoly { ctx: self.ctx.clone(), h }
+    }
+}
+macro_rules! binop { ($name:ident, $f:ident) => {
+    pub fn $name(&self, o: &DevicePoly) -> DevicePoly {
+        let mut h = ptr::null_mut();
+        self.ctx.check(unsafe { $f(self.ctx.0, self.h, o.h, &mut h) });
+        DevicePoly { ctx: self.ctx.clone(), h }
+    } } }
+macro_rules! unop { ($name:ident, $f:ident $(, $a:ident : $t:ty)*) => {
+    pub fn $name(&self $(, $a: $t)*) -> DevicePoly {
+        let mut h = ptr::null_mut();
+        self.ctx.check(unsafe { $f(self.ctx.0, self.h $(, $a)*, &mut h) });
+        DevicePoly { ctx: self.ctx.clone(), h }
+    } } }
+impl DevicePoly {
+    /// `data` must be in standard (row-major, contiguous) layout: call `as_standard_layout()` on the
+    /// ndarray first -- in-place slicing leaves owned arrays strided (multivariate_taylor.rs:85, :176).
+    pub fn from_host(ctx: &Rc<Context>, shape: &[usize], degrees_p1: &[usize], data: &[f64]) -> Self {
+        let s: Vec<u64> = shape.iter().map(|&x| x as u64).collect();
+        let d: Vec<u64> = degrees_p1.iter().map(|&x| if x == usize::MAX { GTP_UNBOUNDED } else { x as u64 }).collect();
+        assert_eq!(data.len(), shape.iter().product::<usize>());
+        let mut h = ptr::null_mut();
+        ctx.check(unsafe { gtp_from_host(ctx.0, s.len() as c_int, s.as_ptr(), d.as_ptr(), data.as_ptr(), &mut h) });
+        DevicePoly { ctx: ctx.clone(), h }
+    }
+    pub fn to_host(&self) -> (Vec<usize>, Vec<f64>) {
+        let n = unsafe { gtp_ndim(self.h) } as usize;
+        let mut s = vec![0u64; n.max(1)];
+        unsafe { gtp_shape(self.h, s.as_mut_ptr()) };
+        let mut out = vec![0f64; unsafe { gtp_len(self.h) } as usize];
+        self.ctx.check(unsafe { gtp_to_host(self.ctx.0, self.h, out.as_mut_ptr()) });
+        (s[..n].iter().map(|&x| x as usize).collect(), out)
+    }
+    binop!(add, gtp_add); binop!(sub, gtp_sub); binop!(mul, gtp_mul); binop!(div, gtp_div);
+    unop!(neg, gtp_neg); unop!(exp, gtp_exp); unop!(log, gtp_log); unop!(pow, gtp_pow, e: u32);
+    unop!(derivative, gtp_derivative, v: u64, n: u64);
+    unop!(taylor_expansion_of_coeff, gtp_taylor_expansion_of_coeff, v: u64, n: u64);
+    unop!(shift_down, gtp_shift_down, v: u64, n: u64);
+    unop!(coefficients_of_term, gtp_coefficients_of_term, v: u64, order: u64);
+    unop!(truncate_to_degree_p1, gtp_truncate_to_degree_p1, d: u64);
+    unop!(remove_last_variable, gtp_remove_last_variable);
+    unop!(extend_to_dim, gtp_extend_to_dim, ndim: u64, d: u64);
+    pub fn subst_var(&self, v: u64, subst: &DevicePoly) -> DevicePoly {
+        let mut h = ptr::null_mut();
+        self.ctx.check(unsafe { gtp_subst_var(self.ctx.0, self.h, v, subst.h, &mut h) });
+        DevicePoly { ctx: self.ctx.clone(), h }
+    }
+    pub fn constant_term(&self) -> f64 {
+        let mut x = 0.0;
+        self.ctx.check(unsafe { gtp_constant_term(self.ctx.0, self.h, &mut x) });
+        x
+    }
+    /// probs_taylor / moments_taylor read `limit` coefficients along one axis
+    /// (generating_function.rs:959-965, :988-993): ONE gather + ONE copy instead of `limit` round trips.
+    pub fn gather_axis(&self, v: u64, count: usize) -> Vec<f64> {
+        let mut out = vec![0f64; count];
+        self.ctx.check(unsafe { gtp_gather_axis(self.ctx.0, self.h, v, count as u64, out.as_mut_ptr()) });
+        out
+    }
+}
