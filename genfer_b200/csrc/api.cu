@@ -672,7 +672,7 @@ void* gtp_ctx_stream(gtp_ctx* c) { return c ? (void*)c->stream : nullptr; }
 uint64_t gtp_ctx_launch_count(gtp_ctx* c) { return c ? c->launches : 0; }
 int gtp_ctx_set_fast_mul(gtp_ctx* c, int enabled) {
   if (!c) return GTP_ERR_ARG;
-  c->fast_mul = enabled != 0;
+  c->fast_mul = enabled < 0 ? 0 : (enabled > 2 ? 2 : enabled);
   return GTP_OK;
 }
 

@@ -85,9 +85,9 @@ void launch_gather_strided(Ctx& ctx, const double* in, u64 stride, u64 len, u64 
 struct MulArgs {
   int ndim;
   Shape xs, ys, rs;
-  const double* x;
-  const double* y;
-  double* out;
+  const double* x = nullptr;
+  const double* y = nullptr;
+  double* out = nullptr;
   u64 row_begin = 0, row_step = 1, row_count = 0;
   std::vector<u64> rows;  // explicit leading-axis row list (overrides begin/step/count when non-empty)
   bool accumulate = false;

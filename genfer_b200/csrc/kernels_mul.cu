@@ -109,9 +109,23 @@ double mul_macs(const Shape& xs, const Shape& ys, const Shape& rs) {
 
 // implemented in kernels_mul_fast.cu
 bool fast_mul_applicable(const Ctx& ctx, const MulArgs& a);
+bool fast_mul_cube16(const Ctx& ctx, const MulArgs& a);
 void launch_mul_fast(Ctx& ctx, const MulArgs& a);
 
-int mul_kernel_kind(const Ctx& ctx, const MulArgs& a) { return (ctx.fast_mul && fast_mul_applicable(ctx, a)) ? 1 : 0; }
+// implemented in kernels_mul_blk.cu
+bool blk_mul_applicable(const Ctx& ctx, const MulArgs& a);
+void launch_mul_blk(Ctx& ctx, const MulArgs& a);
+
+// 0: reference-order kernel, 1: register-tiled cube kernel (kernels_mul_fast.cu), 2: generic blocked kernel
+int mul_kernel_kind(const Ctx& ctx, const MulArgs& a) {
+  if (!ctx.fast_mul) return 0;
+  if ((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.y)) & 15u) return 0;  // cp.async 16-byte staging
+  const bool blk = blk_mul_applicable(ctx, a);
+  if (ctx.fast_mul == 2 && blk) return 2;
+  if (fast_mul_cube16(ctx, a)) return 1;
+  if (blk) return 2;
+  return fast_mul_applicable(ctx, a) ? 1 : 0;
+}
 
 static void launch_mul_ordered(Ctx& ctx, const MulArgs& a) {
   const int nd = a.ndim;
@@ -174,8 +188,13 @@ void launch_mul(Ctx& ctx, const MulArgs& a_in) {
     a.row_begin = a.rows[0];
     a.row_step = 1;
   }
-  if (mul_kernel_kind(ctx, a) == 1) {
+  const int kind = mul_kernel_kind(ctx, a);
+  if (kind == 1) {
     launch_mul_fast(ctx, a);
+    return;
+  }
+  if (kind == 2) {
+    launch_mul_blk(ctx, a);
     return;
   }
   if (a.rows.empty()) {

@@ -218,6 +218,12 @@ bool fast_mul_applicable(const Ctx&, const MulArgs& a) {
   return slabs >= 64;
 }
 
+bool fast_mul_cube16(const Ctx& ctx, const MulArgs& a) {
+  FastGeom g;
+  if (!fast_mul_applicable(ctx, a) || !fast_geom(a, &g)) return false;
+  return g.lt == 16 && g.xb1 == 16 && g.yb1 == 16 && g.rb1 == 16 && g.xb2 == 16 && g.yb2 == 16 && g.rb2 == 16;
+}
+
 // Balanced step table for one slab-pair product.  Work item = (z row, x row, y row).  Rows are dealt
 // to the 64 lanes longest-first onto the least loaded lane (LPT); a lane's items for one row stay contiguous.
 // Triangular 16x16 slab (the dense-cube case): the k <-> 15-k folding.  Lane (c1,c2), c in 0..7, owns

@@ -65,7 +65,8 @@ class Context:
     def stream(self) -> int:
         return int(self.lib.gtp_ctx_stream(self.h) or 0)
 
-    def set_fast_mul(self, enabled: bool):
+    def set_fast_mul(self, enabled):
+        """0/False: reference-order kernel only; 1/True: fastest applicable; 2: prefer the generic blocked kernel."""
         self.check(self.lib.gtp_ctx_set_fast_mul(self.h, int(enabled)))
 
     def fp64_peak_probe(self, kind: int, iters: int = 4096):

@@ -37,7 +37,7 @@ def gpu_mul_raw(ctx, x, y, rshape, rows=None, fast=True):
     torch.cuda.synchronize()
     ctx.mul_rows_raw(x.shape, xd.data_ptr(), y.shape, yd.data_ptr(), rshape, begin, step, count, out.data_ptr())
     ctx.synchronize()
-    ctx.set_fast_mul(True)
+    ctx.set_fast_mul(1)
     return out.cpu().numpy()
 
 
@@ -75,6 +75,37 @@ def test_ragged_product_matches_oracle(ctx, xs, ys, rs):
     got = gpu_mul_raw(ctx, x, y, rs, fast=False)
     assert np.array_equal(got.view(np.uint64), ref.view(np.uint64))
     got = gpu_mul_raw(ctx, x, y, rs, fast=True)
+    np.testing.assert_allclose(got, ref, rtol=1e-11, atol=1e-12)
+
+
+BLK_CUBES = [(4, 8), (4, 10), (4, 12), (4, 14), (4, 16), (3, 32), (3, 24), (4, 20), (3, 28), (3, 48), (4, 24), (5, 8), (5, 12)]
+
+
+@pytest.mark.parametrize("n,d", BLK_CUBES)
+def test_blocked_kernel_cubes_match_oracle(ctx, n, d):
+    """The generic 2x2-blocked kernel (mode 2 forces it): every chunk length 8..16, chunked last axes
+    (20 = 2x10, 24 = 2x12, 28 = 2x14, 32 = 2x16, 48 = 3x16), folded and unfolded b1."""
+    from oracle import oracle as O
+    x, y = synth_pgf((d,) * n, 20230517), synth_uniform((d,) * n, 20231210)
+    ref = O.mul_raw(x, y, (d,) * n)
+    got = gpu_mul_raw(ctx, x, y, (d,) * n, fast=2)
+    assert rel_err(got, ref) <= RTOL, rel_err(got, ref)
+
+
+BLK_RAGGED = [((5, 7, 9, 16), (6, 4, 9, 16), (8, 9, 12, 16)), ((3, 5, 16), (4, 2, 16), (6, 6, 16)),
+              ((4, 4, 5, 24), (2, 3, 7, 24), (5, 4, 9, 24)), ((16, 16, 1, 8), (16, 1, 16, 8), (16, 16, 16, 8)),
+              ((7, 3, 12), (7, 5, 12), (7, 7, 12)), ((2, 9, 9, 32), (3, 9, 9, 32), (4, 9, 5, 32)),
+              ((6, 1, 1, 10), (6, 1, 1, 10), (6, 1, 1, 10))]
+
+
+@pytest.mark.parametrize("xs,ys,rs", BLK_RAGGED)
+def test_blocked_kernel_ragged_match_oracle(ctx, xs, ys, rs):
+    """Odd row counts (zero-filled pair rows), result shorter / longer than the operands, unit axes."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(5)
+    x, y = rng.standard_normal(xs), rng.standard_normal(ys)
+    ref = O.mul_raw(x, y, rs)
+    got = gpu_mul_raw(ctx, x, y, rs, fast=2)
     np.testing.assert_allclose(got, ref, rtol=1e-11, atol=1e-12)
 
 
