@@ -672,6 +672,10 @@ void* gtp_ctx_stream(gtp_ctx* c) { return c ? (void*)c->stream : nullptr; }
 uint64_t gtp_ctx_launch_count(gtp_ctx* c) { return c ? c->launches : 0; }
 int gtp_ctx_set_fast_mul(gtp_ctx* c, int enabled) {
   if (!c) return GTP_ERR_ARG;
+  // bit 2 (value 4) switches the blocked kernel's structured item tables off (A/B measurements)
+  c->blk_fold_tables = (enabled & 4) == 0;
+  c->blk_octet = (enabled & 8) != 0;   // experimental
+  enabled &= 3;
   c->fast_mul = enabled < 0 ? 0 : (enabled > 2 ? 2 : enabled);
   return GTP_OK;
 }

@@ -85,9 +85,10 @@ struct Ctx {
   double* gather_host = nullptr;        // pinned, for gtp_gather_axis / to_host staging
   u64 gather_cap = 0;
   u64 launches = 0;
-  int fast_mul = 1;  // 0: reference-order kernel only, 1: auto, 2: prefer the generic blocked kernel over the cube16 one
-  std::shared_ptr<void> fast_plans;  // per-context cache of product plans (kernels_mul_fast.cu)
-  std::shared_ptr<void> blk_plans;   // same for kernels_mul_blk.cu
+  int fast_mul = 1;  // 0: reference-order kernel only, 1: auto, 2: force the blocked kernel even on tiny products (tests)
+  std::shared_ptr<void> blk_plans;   // per-context cache of product plans (kernels_mul_blk.cu)
+  bool blk_octet = false;            // experimental octet tables for single-plane slabs (8 staged pairs = 8 lanes)
+  bool blk_fold_tables = true;       // structured (folded) item tables for dense cube slabs; false: evenly dealt
 
   BufP alloc(u64 n_doubles);
   void sync() { GTP_CUDA(cudaStreamSynchronize(stream)); }

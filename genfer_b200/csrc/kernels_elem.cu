@@ -265,6 +265,61 @@ __global__ void __launch_bounds__(256) k_shift_down_lanes(const double* __restri
   }
 }
 
+// contiguous SHORT lanes (len <= 64, the cube case): a CTA stages a tile of 256 whole lanes in shared memory with
+// coalesced 16-byte loads (the tile is one contiguous span of HBM), then thread i folds lane i in exactly the
+// order of the 8-threads-per-lane kernel above (p_0..p_7 strided partials, (p_l + p_{l+4}) combined in order,
+// sequential tail), and the surviving slices are written back as one contiguous span.  The lane stride in
+// shared memory is odd (in doubles) so the 64-bit row reads of a half-warp hit 16 distinct bank pairs.
+constexpr int SD_LANES = 256;
+__global__ void __launch_bounds__(SD_LANES) k_shift_down_tile(const double* __restrict__ in, double* __restrict__ out,
+                                                             u64 outer, unsigned len, unsigned n, unsigned out_len, unsigned pad) {
+  extern __shared__ double tile[];
+  const u64 lane0 = (u64)blockIdx.x * SD_LANES;
+  const unsigned lanes = (unsigned)min((u64)SD_LANES, outer - lane0);
+  const double* src = in + lane0 * len;
+  const unsigned total = lanes * len;
+  if ((len & 1u) == 0) {   // rows hold an even number of doubles: the span is 16-byte aligned with the tensor
+    const double2* src2 = reinterpret_cast<const double2*>(src);
+    for (unsigned e = threadIdx.x; e < total / 2; e += SD_LANES) {
+      double2 v = src2[e];
+      unsigned o = (2 * e) / len, a = 2 * e - o * len;
+      tile[o * pad + a] = v.x;
+      tile[o * pad + a + 1] = v.y;
+    }
+  } else {
+    for (unsigned e = threadIdx.x; e < total; e += SD_LANES) {
+      unsigned o = e / len, a = e - o * len;
+      tile[o * pad + a] = src[e];
+    }
+  }
+  __syncthreads();
+  const unsigned head = (len <= n + 1) ? len : n;
+  if (threadIdx.x < lanes) {
+    double* row = tile + threadIdx.x * pad;
+    double p[8];
+#pragma unroll
+    for (int l = 0; l < 8; l++) p[l] = 0.0;
+    const unsigned chunks = head / 8;
+    for (unsigned c = 0; c < chunks; c++) {
+#pragma unroll
+      for (int l = 0; l < 8; l++) p[l] = __dadd_rn(p[l], row[c * 8 + l]);
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int l = 0; l < 4; l++) acc = __dadd_rn(acc, __dadd_rn(p[l], p[l + 4]));
+    for (unsigned a = chunks * 8; a < head; a++) acc = __dadd_rn(acc, row[a]);
+    if (len <= n + 1) row[len - 1] = acc;                 // the single surviving slice
+    else row[n] = __dadd_rn(row[n], acc);
+  }
+  __syncthreads();
+  const unsigned first = (len <= n + 1) ? len - 1 : n;
+  double* dst = out + lane0 * out_len;
+  for (unsigned e = threadIdx.x; e < lanes * out_len; e += SD_LANES) {
+    unsigned o = e / out_len, k = e - o * out_len;
+    dst[e] = tile[o * pad + first + k];
+  }
+}
+
 void launch_shift_down(Ctx& ctx, const double* in, double* out, u64 outer, u64 len, u64 inner, u64 n,
                        bool last_axis) {
   u64 out_len = (len <= n + 1) ? 1 : len - n;
@@ -272,6 +327,17 @@ void launch_shift_down(Ctx& ctx, const double* in, double* out, u64 outer, u64 l
     u64 total = outer * inner;
     int grid = (int)std::max<u64>(1, std::min<u64>((total + 255) / 256, (u64)ctx.sm_count * 32));
     GTP_LAUNCH(ctx, k_shift_down_strided, grid, 256, 0, in, out, outer, len, inner, n, out_len);
+  } else if (len <= 64 && outer >= 1024 && (reinterpret_cast<uintptr_t>(in) & 15u) == 0 &&
+             (outer + SD_LANES - 1) / SD_LANES < (1u << 31)) {
+    unsigned pad = (unsigned)((len & 1) ? len : len + 1);
+    size_t smem = (size_t)SD_LANES * pad * sizeof(double);
+    static bool configured[64] = {};
+    if (!configured[ctx.device & 63]) {
+      GTP_CUDA(cudaFuncSetAttribute(k_shift_down_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, SD_LANES * 65 * 8));
+      configured[ctx.device & 63] = true;
+    }
+    unsigned grid = (unsigned)((outer + SD_LANES - 1) / SD_LANES);
+    GTP_LAUNCH(ctx, k_shift_down_tile, grid, SD_LANES, smem, in, out, outer, (unsigned)len, (unsigned)n, (unsigned)out_len, pad);
   } else {
     u64 lanes_per_block = 256 / 8;
     int grid = (int)std::max<u64>(1, std::min<u64>((outer + lanes_per_block - 1) / lanes_per_block, (u64)ctx.sm_count * 32));

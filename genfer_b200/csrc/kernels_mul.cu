@@ -5,8 +5,8 @@
 // coefficient.  It performs the multiply and the add separately (DMUL + DADD, no FMA) and
 // in exactly the reference's nesting order -- outer axes ascending, the innermost non-unit axis
 // summed from zero and then added (mul_1d :972-982 feeding `*z += o` :998) -- so its results are
-// bit-identical to the reference f64 path.  The register-tiled DFMA kernel for dense cubes lives in
-// kernels_mul_fast.cu; launch_mul() picks between them.
+// bit-identical to the reference f64 path.  The register-blocked DFMA kernel lives in kernels_mul_blk.cu;
+// launch_mul() picks between them.
 #include "kernels.cuh"
 
 namespace gtp {
@@ -107,24 +107,16 @@ double mul_macs(const Shape& xs, const Shape& ys, const Shape& rs) {
   return total;
 }
 
-// implemented in kernels_mul_fast.cu
-bool fast_mul_applicable(const Ctx& ctx, const MulArgs& a);
-bool fast_mul_cube16(const Ctx& ctx, const MulArgs& a);
-void launch_mul_fast(Ctx& ctx, const MulArgs& a);
-
 // implemented in kernels_mul_blk.cu
 bool blk_mul_applicable(const Ctx& ctx, const MulArgs& a);
 void launch_mul_blk(Ctx& ctx, const MulArgs& a);
 
-// 0: reference-order kernel, 1: register-tiled cube kernel (kernels_mul_fast.cu), 2: generic blocked kernel
+// 0: reference-order kernel, 2: 2x2-blocked DFMA kernel (kernels_mul_blk.cu).  (1 was the cube-16-only kernel of
+// the first round; the blocked kernel with folded tables superseded it.)
 int mul_kernel_kind(const Ctx& ctx, const MulArgs& a) {
   if (!ctx.fast_mul) return 0;
   if ((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.y)) & 15u) return 0;  // cp.async 16-byte staging
-  const bool blk = blk_mul_applicable(ctx, a);
-  if (ctx.fast_mul == 2 && blk) return 2;
-  if (fast_mul_cube16(ctx, a)) return 1;
-  if (blk) return 2;
-  return fast_mul_applicable(ctx, a) ? 1 : 0;
+  return blk_mul_applicable(ctx, a) ? 2 : 0;
 }
 
 static void launch_mul_ordered(Ctx& ctx, const MulArgs& a) {
@@ -189,10 +181,6 @@ void launch_mul(Ctx& ctx, const MulArgs& a_in) {
     a.row_step = 1;
   }
   const int kind = mul_kernel_kind(ctx, a);
-  if (kind == 1) {
-    launch_mul_fast(ctx, a);
-    return;
-  }
   if (kind == 2) {
     launch_mul_blk(ctx, a);
     return;

@@ -24,7 +24,7 @@
 
 namespace gtp {
 
-constexpr int BT = 128;       // threads per CTA
+constexpr int BT = 128;       // threads per CTA (256 in octet mode when 8 slab pairs need a whole SM's shared memory)
 constexpr int B_MAXA = 6;
 constexpr int B_MAXG = 8;
 
@@ -42,6 +42,7 @@ struct BlkP {
   unsigned x_slab_sm, y_slab_sm;                 // per staged slab
   unsigned x_pair_off, y_pair_off;               // distance between the two rows of a pair (Lc*ROW)
   int G;
+  int octet;               // 1: table has one column per 8-thread octet, lane = staged slab g (see build_octet_table)
   int nsteps_lo, nsteps;   // steps [0, nsteps_lo) hold `lo` items, [nsteps_lo, nsteps) `hi` items
   const uint2* table;    // [nsteps][BT]
   const uint4* units;    // {packed kA index, q0, q1, k along A axis 0}
@@ -112,19 +113,25 @@ __device__ __forceinline__ void blk_item(double (&z0)[LT], double (&z1)[LT], dou
 }
 
 template <int LT, bool CHUNKED>
-__global__ void __launch_bounds__(BT, 2) k_mul_blk(const BlkP p) {
+__global__ void __launch_bounds__(256) k_mul_blk(const BlkP p) {
   constexpr int ROW = BRow<LT>::value;
   constexpr int V2 = LT / 2;
   extern __shared__ __align__(16) double smem[];
   double* Xs = smem;
   double* Ys = smem + (size_t)p.G * p.x_slab_sm;
   const int tid = threadIdx.x;
+  const int bt = blockDim.x;
   const uint4 unit = p.units[blockIdx.x];
+  // table column of this thread, and the staged slab its entries refer to (octet mode: lane = g)
+  const int tcols = p.octet ? (bt >> 3) : bt;
+  const int tcol = p.octet ? (tid >> 3) : tid;
+  const unsigned lane_g = p.octet ? (unsigned)(tid & 7) : 0u;
+  const unsigned lane_xoff = lane_g * p.x_slab_sm, lane_yoff = lane_g * p.y_slab_sm;
 
   // zero the whole staging area once: padding rows (odd b2) must read as zeros forever
   {
     const int total = p.G * (int)(p.x_slab_sm + p.y_slab_sm);
-    for (int i = tid * 2; i < total; i += BT * 2) *reinterpret_cast<double2*>(smem + i) = make_double2(0.0, 0.0);
+    for (int i = tid * 2; i < total; i += bt * 2) *reinterpret_cast<double2*>(smem + i) = make_double2(0.0, 0.0);
   }
 
   unsigned k[B_MAXA], lo[B_MAXA], ext[B_MAXA];
@@ -175,12 +182,12 @@ __global__ void __launch_bounds__(BT, 2) k_mul_blk(const BlkP p) {
       double* xs = Xs + (size_t)g * p.x_slab_sm;
       double* ys = Ys + (size_t)g * p.y_slab_sm;
       const int nx = (int)(p.x_planes * p.x_prow) * V2, ny = (int)(p.y_planes * p.y_prow) * V2;
-      for (int i = tid; i < nx; i += BT) {
+      for (int i = tid; i < nx; i += bt) {
         int r = i / V2, c = i - r * V2;
         int pl = r / (int)p.x_prow, rr = r - pl * (int)p.x_prow;
         blk_cp16(xs + pl * p.x_plane_sm + rr * ROW + 2 * c, gx + i);
       }
-      for (int i = tid; i < ny; i += BT) {
+      for (int i = tid; i < ny; i += bt) {
         int r = i / V2, c = i - r * V2;
         int pl = r / (int)p.y_prow, rr = r - pl * (int)p.y_prow;
         blk_cp16(ys + pl * p.y_plane_sm + rr * ROW + 2 * c, gy + i);
@@ -201,12 +208,12 @@ __global__ void __launch_bounds__(BT, 2) k_mul_blk(const BlkP p) {
       if (cnt <= 0) continue;
       int step = fwd ? s_begin : s_end - 1;
       const int dstep = fwd ? 1 : -1;
-      uint2 e = p.table[step * BT + tid];
+      uint2 e = p.table[step * tcols + tcol];
       for (int s = 0; s < cnt; ++s) {
         step += dstep;
         uint2 en = make_uint2(0u, 0u);
-        if (s + 1 < cnt) en = p.table[step * BT + tid];
-        if ((e.x & BE_VALID) && (int)((e.x >> 20) & 15u) < ng) {
+        if (s + 1 < cnt) en = p.table[step * tcols + tcol];
+        if ((e.x & BE_VALID) && (int)(((e.x >> 20) & 15u) + lane_g) < ng) {
           const unsigned zkey = ((e.y >> 20) << 2) | ((e.x >> 25) & 3u);
           if (zkey != cur) {
             if (cur != 0xffffffffu) {
@@ -217,8 +224,8 @@ __global__ void __launch_bounds__(BT, 2) k_mul_blk(const BlkP p) {
             }
             cur = zkey;
           }
-          const double* xs = Xs + (e.x & 0xfffffu);
-          const double* ys = Ys + (e.y & 0xfffffu);
+          const double* xs = Xs + (e.x & 0xfffffu) + lane_xoff;
+          const double* ys = Ys + (e.y & 0xfffffu) + lane_yoff;
           if (hi) blk_item<LT, true>(z0, z1, z2, xs, xs + p.x_pair_off, ys, ys + p.y_pair_off);
           else blk_item<LT, false>(z0, z1, z2, xs, xs + p.x_pair_off, ys, ys + p.y_pair_off);
         }
@@ -245,8 +252,13 @@ struct BlkGeom {
   u64 row;             // padded row length in smem (doubles)
   u64 xplane, yplane, xslab, yslab;   // smem strides (doubles)
   int G;
+  int bt;              // threads per CTA
+  bool octet;          // lanes of an 8-thread octet = the 8 staged slab pairs
   size_t smem;
 };
+
+struct BlkGeom;
+static bool blk_dense(const BlkGeom& g);
 
 static u64 pick_chunk(u64 ltt) {
   for (u64 lt : {16, 14, 12, 10, 8})
@@ -254,7 +266,7 @@ static u64 pick_chunk(u64 ltt) {
   return 0;
 }
 
-static bool blk_geom(const MulArgs& a, BlkGeom* g) {
+static bool blk_geom(const MulArgs& a, BlkGeom* g, bool allow_octet = false) {
   const int nd = a.ndim;
   if (nd < 3) return false;
   const u64 ltt = a.rs[nd - 1];
@@ -276,6 +288,9 @@ static bool blk_geom(const MulArgs& a, BlkGeom* g) {
     g->yslab = yb1 * g->yplane + 2;
     g->xslab = (g->xslab + 1) / 2 * 2;
     g->yslab = (g->yslab + 1) / 2 * 2;
+    // staged slabs g = 0..G-1 start in different 16-byte bank groups: slab stride = odd number of groups
+    if ((g->xslab / 2) % 2 == 0) g->xslab += 2;
+    if ((g->yslab / 2) % 2 == 0) g->yslab += 2;
   };
   // try the 3-axis slab first
   const size_t budget = 100 * 1024;   // two CTAs per SM
@@ -297,6 +312,17 @@ static bool blk_geom(const MulArgs& a, BlkGeom* g) {
   const u64 pair = (g->xslab + g->yslab) * 8;
   if (pair > budget) return false;
   g->G = (int)std::max<u64>(1, std::min<u64>(B_MAXG, budget / pair));
+  g->bt = BT;
+  g->octet = false;
+  if (g->fold_b1 && allow_octet) {
+    // (experimental, off by default: conflict-free but RED-bound)
+    // single-plane slabs: stage 8 pairs and let the 8 lanes of an octet run the same item on the 8 pairs
+    if (8 * pair <= budget) {
+      g->G = 8; g->octet = true;
+    } else if (8 * pair <= 200 * 1024) {
+      g->G = 8; g->octet = true; g->bt = 256;   // one 256-thread CTA per SM
+    }
+  }
   if (g->G * std::max(g->xslab, g->yslab) >= (1u << 20)) return false;
   g->smem = (size_t)g->G * pair;
   return true;
@@ -352,8 +378,117 @@ static void build_items(const BlkGeom& g, std::vector<std::vector<BlkItem>>* blo
   }
 }
 
+static bool blk_dense(const BlkGeom& g) {
+  return g.xb1 == g.rb1 && g.yb1 == g.rb1 && g.xb2 == g.rb2 && g.yb2 == g.rb2 && g.rb2 % 4 == 0 &&
+         (g.fold_b1 || g.rb1 % 2 == 0);
+}
+
+static uint2 blk_entry(const BlkGeom& g, const BlkItem& it, int gi) {
+  uint2 e;
+  e.x = (it.xoff + (unsigned)(gi * g.xslab)) | ((unsigned)gi << 20) | (it.kind << 24) | (it.zv << 25) | BE_VALID;
+  e.y = (it.yoff + (unsigned)(gi * g.yslab)) | (it.zrow << 20);
+  return e;
+}
+
+// Structured ("folded") table for dense cube slabs: X, Y and Z have the same even plane count D1 (or the slab
+// is a single plane) and the same row count D2 = 2P with P even.  A lane is (c1, d[, g]):
+//   c1 in 0..D1/2-1 : owns output planes c1 and D1-1-c1  -> D1+1 plane steps (s1 <= c1: plane c1, j1 = s1;
+//                                                            s1 > c1: plane D1-1-c1, j1 = s1-c1-1)
+//   d  in 0..P/2-1  : owns output row pairs d and P-1-d  -> P+1 pair steps (ap = 0..half, bp = half-ap)
+// so every lane executes exactly the same number of items per slab pair, of the same kinds in the same order,
+// and touches only 4*Lc output row blocks.  Lanes of a quarter-warp differ only in c1 (3-axis slab) or in the
+// staged slab g (single-plane slab): the rows they read at one step are either identical (broadcast) or lie in
+// different planes / slabs, whose strides are odd multiples of 16 bytes -> (almost) conflict-free LDS.128.
+// T teams share a lane's sequence round-robin (thread = team*lanes + lane).
+static bool build_fold_table(const BlkGeom& g, std::vector<uint2>* table, int* n_lo, int* n_hi) {
+  if (!blk_dense(g) || g.fold_b1 || g.octet) return false;
+  const int D1 = (int)g.rb1, P = (int)(g.rb2 / 2);
+  const int C1 = D1 / 2, DD = P / 2;
+  const int nl = C1 * DD;
+  if (nl > BT || nl < 16) return false;
+  const int T = BT / nl;
+  std::vector<std::vector<uint2>> seq_lo(nl), seq_hi(nl);
+  for (int d = 0; d < DD; d++)
+    for (int c1 = 0; c1 < C1; c1++) {
+      const int lane = d * C1 + c1;
+      int seam = 0;
+      for (int phase = 0; phase < 2; phase++) {
+        const int half = phase == 0 ? d : P - 1 - d;
+        const int s = 2 * half;
+        for (int kc = 0; kc < (int)g.lc; kc++)
+          for (int gi = 0; gi < g.G; gi++, seam++)
+            // D1+1 plane steps in lockstep over the lanes: t <= c1 -> plane c1, j1 = t; t > c1 -> plane D1-1-c1,
+            // j1 = t-c1-1 (walked backwards on odd seams so the plane at the seam stays in registers)
+            for (int tt = 0; tt <= D1; tt++) {
+              const int t = (seam & 1) ? D1 - tt : tt;
+              const int r1 = t <= c1 ? c1 : D1 - 1 - c1;
+              const int j1 = t <= c1 ? t : t - c1 - 1;
+              for (int ap = 0; ap <= half; ap++) {
+                const int bp = half - ap;
+                for (int jc = 0; jc < (int)g.lc; jc++)
+                  for (int mc = 0; mc < (int)g.lc; mc++) {
+                    unsigned kind;
+                    if (jc + mc == kc) kind = 0;
+                    else if (jc + mc + 1 == kc) kind = 1;
+                    else continue;
+                    BlkItem it;
+                    it.xoff = (unsigned)(j1 * g.xplane + (2 * ap * g.lc + jc) * g.row);
+                    it.yoff = (unsigned)((r1 - j1) * g.yplane + (2 * bp * g.lc + mc) * g.row);
+                    it.zrow = (unsigned)(((u64)r1 * g.rb2 + s) * g.lc + kc);
+                    it.kind = kind;
+                    it.zv = ((u64)s + 1 < g.rb2 ? 1u : 0u) | ((u64)s + 2 < g.rb2 ? 2u : 0u);
+                    (kind ? seq_hi : seq_lo)[lane].push_back(blk_entry(g, it, gi));
+                  }
+              }
+            }
+      }
+    }
+  const size_t len_lo = seq_lo[0].size(), len_hi = seq_hi[0].size();
+  for (int l = 0; l < nl; l++)
+    if (seq_lo[l].size() != len_lo || seq_hi[l].size() != len_hi) return false;   // not a perfect fold
+  *n_lo = (int)((len_lo + T - 1) / T);
+  *n_hi = (int)((len_hi + T - 1) / T);
+  table->assign((size_t)std::max(*n_lo + *n_hi, 1) * BT, make_uint2(0u, 0u));
+  // each team takes a CONTIGUOUS share of the lane's sequence: few output-block changes per thread
+  for (int team = 0; team < T; team++)
+    for (int l = 0; l < nl; l++) {
+      const int tid = team * nl + l;
+      size_t b = len_lo * team / T, e = len_lo * (team + 1) / T;
+      for (size_t i = b; i < e; i++) (*table)[(i - b) * BT + tid] = seq_lo[l][i];
+      b = len_hi * team / T, e = len_hi * (team + 1) / T;
+      for (size_t i = b; i < e; i++) (*table)[((size_t)*n_lo + (i - b)) * BT + tid] = seq_hi[l][i];
+    }
+  return true;
+}
+
+// Octet table for single-plane slabs with 8 staged pairs: ONE column per octet (8 consecutive threads); the
+// lanes of an octet execute the same item on the 8 staged slab pairs g = 0..7, whose strides are odd multiples
+// of 16 bytes => every LDS.128 of a quarter-warp is conflict-free for ANY shape.  The z-block-major item list
+// of one slab pair is dealt evenly to the octets, so an octet changes output block (and flushes) only at the
+// few block boundaries inside its share, and keeps its block in registers from round to round.
+static void build_octet_table(const BlkGeom& g, std::vector<uint2>* table, int* n_lo, int* n_hi) {
+  std::vector<std::vector<BlkItem>> blocks;
+  build_items(g, &blocks);
+  std::vector<uint2> seq[2];
+  for (const auto& blk : blocks)
+    for (const BlkItem& it : blk) seq[it.kind].push_back(blk_entry(g, it, 0));
+  const int cols = g.bt / 8;
+  *n_lo = (int)((seq[0].size() + cols - 1) / cols);
+  *n_hi = (int)((seq[1].size() + cols - 1) / cols);
+  table->assign((size_t)std::max(*n_lo + *n_hi, 1) * cols, make_uint2(0u, 0u));
+  for (int kind = 0; kind < 2; kind++) {
+    const size_t T = seq[kind].size();
+    const size_t base = kind ? (size_t)*n_lo : 0;
+    for (int t = 0; t < cols; t++) {
+      size_t b = T * t / cols, e = T * (t + 1) / cols;
+      for (size_t i = b; i < e; i++) (*table)[(base + (i - b)) * cols + t] = seq[kind][i];
+    }
+  }
+}
+
 struct BlkPlan {
   BufP table, units;
+  bool folded = false;
   unsigned n_units = 0;
   BlkP p;
   BlkGeom g;
@@ -376,13 +511,13 @@ template <int LT> static void blk_launch_lt(Ctx& ctx, const BlkPlan& pl, const B
     else GTP_CUDA(cudaFuncSetAttribute(k_mul_blk<LT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.g.smem));
     configured[ch][ctx.device & 63] = pl.g.smem;
   }
-  if (ch) GTP_LAUNCH(ctx, (k_mul_blk<LT, true>), pl.n_units, BT, pl.g.smem, p);
-  else GTP_LAUNCH(ctx, (k_mul_blk<LT, false>), pl.n_units, BT, pl.g.smem, p);
+  if (ch) GTP_LAUNCH(ctx, (k_mul_blk<LT, true>), pl.n_units, pl.g.bt, pl.g.smem, p);
+  else GTP_LAUNCH(ctx, (k_mul_blk<LT, false>), pl.n_units, pl.g.bt, pl.g.smem, p);
 }
 
 void launch_mul_blk(Ctx& ctx, const MulArgs& a) {
   BlkGeom g;
-  GTP_CHECK(blk_geom(a, &g), GTP_ERR_ARG, "blocked product kernel not applicable");
+  GTP_CHECK(blk_geom(a, &g, ctx.blk_octet), GTP_ERR_ARG, "blocked product kernel not applicable");
   BlkKey key;
   key.v.insert(key.v.end(), a.xs.begin(), a.xs.end());
   key.v.insert(key.v.end(), a.ys.begin(), a.ys.end());
@@ -390,6 +525,7 @@ void launch_mul_blk(Ctx& ctx, const MulArgs& a) {
   key.v.push_back(a.row_begin);
   key.v.push_back(a.row_step);
   key.v.push_back(a.row_count);
+  key.v.push_back((ctx.blk_fold_tables ? 1 : 0) | (ctx.blk_octet ? 2 : 0));
   key.v.insert(key.v.end(), a.rows.begin(), a.rows.end());
   auto& cache = blk_cache(ctx);
   std::shared_ptr<BlkPlan> pl;
@@ -425,29 +561,33 @@ void launch_mul_blk(Ctx& ctx, const MulArgs& a) {
     p.x_pair_off = p.y_pair_off = (unsigned)(g.lc * g.row);
     p.G = g.G;
     // ---- item table: z-block major, then g, then the block's items; dealt evenly to the threads ----
-    std::vector<std::vector<BlkItem>> blocks;
-    build_items(g, &blocks);
-    std::vector<uint2> seq[2];   // by kind
-    for (const auto& blk : blocks)
-      for (int gi = 0; gi < g.G; gi++)
-        for (const BlkItem& it : blk) {
-          uint2 e;
-          e.x = (it.xoff + (unsigned)(gi * g.xslab)) | ((unsigned)gi << 20) | (it.kind << 24) | (it.zv << 25) | BE_VALID;
-          e.y = (it.yoff + (unsigned)(gi * g.yslab)) | (it.zrow << 20);
-          seq[it.kind].push_back(e);
+    std::vector<uint2> table;
+    int n_lo = 0, n_hi = 0;
+    p.octet = g.octet ? 1 : 0;
+    pl->folded = ctx.blk_fold_tables && build_fold_table(g, &table, &n_lo, &n_hi);
+    if (g.octet) {
+      build_octet_table(g, &table, &n_lo, &n_hi);
+    } else if (!pl->folded) {
+      std::vector<std::vector<BlkItem>> blocks;
+      build_items(g, &blocks);
+      std::vector<uint2> seq[2];   // by kind
+      for (const auto& blk : blocks)
+        for (int gi = 0; gi < g.G; gi++)
+          for (const BlkItem& it : blk) seq[it.kind].push_back(blk_entry(g, it, gi));
+      n_lo = (int)((seq[0].size() + BT - 1) / BT);
+      n_hi = (int)((seq[1].size() + BT - 1) / BT);
+      table.assign((size_t)std::max(n_lo + n_hi, 1) * BT, make_uint2(0u, 0u));
+      for (int kind = 0; kind < 2; kind++) {
+        const size_t T = seq[kind].size();
+        const size_t base = kind ? (size_t)n_lo : 0;
+        for (int t = 0; t < BT; t++) {
+          size_t b = T * t / BT, e = T * (t + 1) / BT;
+          for (size_t i = b; i < e; i++) table[(base + (i - b)) * BT + t] = seq[kind][i];
         }
-    const int n_lo = (int)((seq[0].size() + BT - 1) / BT), n_hi = (int)((seq[1].size() + BT - 1) / BT);
-    p.nsteps_lo = n_lo;
-    p.nsteps = n_lo + n_hi;
-    std::vector<uint2> table((size_t)std::max(p.nsteps, 1) * BT, make_uint2(0u, 0u));
-    for (int kind = 0; kind < 2; kind++) {
-      const size_t T = seq[kind].size();
-      const size_t base = kind ? (size_t)n_lo : 0;
-      for (int t = 0; t < BT; t++) {
-        size_t b = T * t / BT, e = T * (t + 1) / BT;
-        for (size_t i = b; i < e; i++) table[(base + (i - b)) * BT + t] = seq[kind][i];
       }
     }
+    p.nsteps_lo = n_lo;
+    p.nsteps = n_lo + n_hi;
     // ---- work units ----
     u64 n_slabs = a.row_count;
     for (int d = 1; d < na; d++) n_slabs *= a.rs[d];
@@ -471,7 +611,7 @@ void launch_mul_blk(Ctx& ctx, const MulArgs& a) {
       boxes[s] = box;
       total_pairs += box;
     }
-    u64 slots = (u64)ctx.sm_count * 2;
+    u64 slots = (u64)ctx.sm_count * (g.bt == 256 ? 1 : 2);
     u64 chunk = std::max<u64>(8 * g.G, total_pairs / (slots * 16) + 1);
     chunk = (chunk + g.G - 1) / g.G * g.G;   // whole rounds
     for (u64 s = 0; s < n_slabs; s++) {

@@ -64,7 +64,8 @@ void* gtp_ctx_stream(gtp_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t gtp_ctx_launch_count(gtp_ctx* ctx);
 /* tuning knob: 0 = always use the reference-order product kernel (bit-exact), 1 = pick the fastest
- * applicable kernel (default), 2 = prefer the generic blocked kernel over the cube-16 specialisation */
+ * applicable kernel (default), 2 = use the blocked DFMA kernel even for tiny products (tests);
+ * +4 = evenly dealt instead of folded item tables (A/B measurements) */
 int gtp_ctx_set_fast_mul(gtp_ctx* ctx, int enabled);
 
 /* ---- construction, transfer, metadata ------------------------------------------------------- */
@@ -147,8 +148,7 @@ int gtp_mul_rowlist_raw(gtp_ctx* ctx, int ndim, const uint64_t* xshape, const do
                         const uint64_t* rows, uint64_t n_rows, double* out_rows);
 /* MAC count of the general product (trip counts of :975-977 and :1002-1004); FLOPs = 2*MACs. */
 double gtp_mul_macs(int ndim, const uint64_t* xshape, const uint64_t* yshape, const uint64_t* rshape);
-/* Which kernel gtp_mul_rows_raw would pick for these shapes: 0 reference-order, 1 cube-16 tiled,
- * 2 generic 2x2-blocked chunked. */
+/* Which kernel gtp_mul_rows_raw would pick for these shapes: 0 reference-order, 2 2x2-blocked DFMA. */
 int gtp_mul_kernel_kind(gtp_ctx* ctx, int ndim, const uint64_t* xshape, const uint64_t* yshape,
                         const uint64_t* rshape);
 /* FP64 pipe microbenchmarks (the roofline denominator): runs `iters` dependent-chain DFMA (kind 0)

@@ -237,6 +237,17 @@ def test_shift_down_long_lanes(G):
         assert_same(g.shift_down(0, min(n, 4)), o.shift_down(0, min(n, 4)))
 
 
+@pytest.mark.parametrize("shape", [(40, 30, 16), (1100, 9), (33, 40, 24), (2048, 64), (1500, 2), (1200, 13)])
+def test_shift_down_short_lanes_tiled(G, shape):
+    """>= 1024 contiguous short lanes take the shared-memory tiled reduction kernel; same fold order, bit-exact."""
+    rng = np.random.default_rng(11)
+    a = rng.standard_normal(shape)
+    g, o = both(G, a)
+    v = len(shape) - 1
+    for n in sorted({0, 1, 7, 8, 9, shape[-1] - 2, shape[-1] - 1} & set(range(0, shape[-1]))):
+        assert_same(g.shift_down(v, n), o.shift_down(v, n))
+
+
 def test_readers_and_panics(G):
     a = np.arange(12, dtype=np.float64).reshape(3, 4) + 1
     g, o = both(G, a, (5, 6))
