@@ -79,6 +79,14 @@ _SIGS = {
     "gtp_mul_macs": (C.c_double, [C.c_int, u64p, u64p, u64p]),
     "gtp_mul_kernel_kind": (C.c_int, [vp, C.c_int, u64p, u64p, u64p]),
     "gtp_fp64_peak_probe": (C.c_int, [vp, C.c_int, C.c_int, f64p, f64p]),
+    "gtp_run_sgcl": (C.c_int, [vp, C.c_char_p, C.c_int64, C.c_int, C.c_uint64, vpp, C.c_char_p, C.c_size_t]),
+    "gtp_sgcl_free": (None, [vp]),
+    "gtp_sgcl_report": (C.c_char_p, [vp]),
+    "gtp_sgcl_moments": (None, [vp, f64p]),
+    "gtp_sgcl_limit": (C.c_uint64, [vp]),
+    "gtp_sgcl_is_normalized": (C.c_int, [vp]),
+    "gtp_sgcl_probs": (None, [vp, f64p, f64p]),
+    "gtp_sgcl_stats": (None, [vp, u64p, u64p]),
     "gtu_constant": (C.c_int, [vp, C.c_double, vpp]),
     "gtu_from_coefficients": (C.c_int, [vp, f64p, C.c_uint64, vpp]),
     "gtu_var": (C.c_int, [vp, C.c_double, C.c_uint64, vpp]),

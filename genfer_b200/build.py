@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgenfer_taylor.so")
-SOURCES = ["api.cu", "api_uni.cu", "kernels_elem.cu", "kernels_mul.cu", "kernels_mul_blk.cu", "kernels_rec.cu",
+SOURCES = ["api.cu", "api_uni.cu", "eval_api.cpp", "kernels_elem.cu", "kernels_mul.cu", "kernels_mul_blk.cu", "kernels_rec.cu",
            "univariate.cu"]
 HEADERS = ["common.hpp", "kernels.cuh", os.path.join("..", "..", "include", "genfer_taylor.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -33,11 +33,13 @@ def _stale(target: str, deps: list[str]) -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
+    import glob
     hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
+    hdrs += glob.glob(os.path.join(CSRC, "evaluator", "*.hpp"))
     objs, procs = [], []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
-        o = os.path.join(objdir, src.replace(".cu", ".o"))
+        o = os.path.join(objdir, src.replace(".cu", ".o").replace(".cpp", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
             cmd = [nvcc(), *NVCC_FLAGS, "-c", s, "-o", o]

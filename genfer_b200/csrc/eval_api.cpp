@@ -1,0 +1,140 @@
+// C ABI of the host evaluator: runs an SGCL program end to end -- parse, translate to a
+// generating function, simplify, evaluate moments and probabilities -- with EVERY Taylor-polynomial operation
+// going through the C ABI of libgenfer_taylor (gtp_*, i.e. the CUDA kernels).  It plays the role of the
+// reference's `run()` / `run_program::<F64>` (src/main.rs:108-227) with GenFun::eval (src/generating_function.rs)
+// as the caller of TaylorPoly.  Host logic only; there is no CPU arithmetic path here: without a CUDA context
+// the calls fail.
+#include <cstring>
+#include <memory>
+
+#include "../../include/genfer_taylor.h"
+#include "evaluator/report.hpp"
+
+namespace {
+
+struct GpuBackend {
+  gtp_ctx* ctx;
+  struct Handle {
+    gtp_ctx* c;
+    gtp_poly* p;
+    Handle(gtp_ctx* c_, gtp_poly* p_) : c(c_), p(p_) {}
+    ~Handle() { if (p) gtp_free(c, p); }
+    Handle(const Handle&) = delete;
+    Handle& operator=(const Handle&) = delete;
+  };
+  using Poly = std::shared_ptr<Handle>;
+
+  void check(int rc) const {
+    if (rc != 0) throw gfe::EvalError(std::string("libgenfer_taylor: ") + gtp_last_error(ctx));
+  }
+  Poly wrap(gtp_poly* p) const { return std::make_shared<Handle>(ctx, p); }
+  static std::vector<uint64_t> u64(const std::vector<size_t>& v) { return std::vector<uint64_t>(v.begin(), v.end()); }
+
+  Poly from_scalar(double x) { gtp_poly* o; check(gtp_from_scalar(ctx, x, &o)); return wrap(o); }
+  Poly var(gfe::Var v, double x, size_t len) { gtp_poly* o; check(gtp_var(ctx, v, x, len, &o)); return wrap(o); }
+  Poly var_at_zero(gfe::Var v, size_t len) { gtp_poly* o; check(gtp_var_at_zero(ctx, v, len, &o)); return wrap(o); }
+  Poly var_with_degrees(gfe::Var v, double x, const std::vector<uint64_t>& d) {
+    gtp_poly* o; check(gtp_var_with_degrees_p1(ctx, v, x, (int)d.size(), d.data(), &o)); return wrap(o);
+  }
+  Poly zero_with(const std::vector<uint64_t>& d) { gtp_poly* o; check(gtp_zero_with(ctx, (int)d.size(), d.data(), &o)); return wrap(o); }
+  Poly new_poly(const std::vector<uint64_t>& shape, const std::vector<uint64_t>& degrees, const double* data) {
+    gtp_poly* o; check(gtp_from_host(ctx, (int)shape.size(), shape.data(), degrees.data(), data, &o)); return wrap(o);
+  }
+#define GFE_BIN(name, fn) Poly name(const Poly& a, const Poly& b) { gtp_poly* o; check(fn(ctx, a->p, b->p, &o)); return wrap(o); }
+  GFE_BIN(add, gtp_add) GFE_BIN(sub, gtp_sub) GFE_BIN(mul, gtp_mul) GFE_BIN(div, gtp_div)
+#undef GFE_BIN
+  Poly neg(const Poly& a) { gtp_poly* o; check(gtp_neg(ctx, a->p, &o)); return wrap(o); }
+  Poly exp(const Poly& a) { gtp_poly* o; check(gtp_exp(ctx, a->p, &o)); return wrap(o); }
+  Poly log(const Poly& a) { gtp_poly* o; check(gtp_log(ctx, a->p, &o)); return wrap(o); }
+  Poly pow(const Poly& a, uint32_t e) { gtp_poly* o; check(gtp_pow(ctx, a->p, e, &o)); return wrap(o); }
+  Poly derivative(const Poly& a, gfe::Var v, size_t n) { gtp_poly* o; check(gtp_derivative(ctx, a->p, v, n, &o)); return wrap(o); }
+  Poly taylor_expansion_of_coeff(const Poly& a, gfe::Var v, size_t n) { gtp_poly* o; check(gtp_taylor_expansion_of_coeff(ctx, a->p, v, n, &o)); return wrap(o); }
+  Poly shift_down(const Poly& a, gfe::Var v, size_t n) { gtp_poly* o; check(gtp_shift_down(ctx, a->p, v, n, &o)); return wrap(o); }
+  Poly coefficients_of_term(const Poly& a, gfe::Var v, size_t n) { gtp_poly* o; check(gtp_coefficients_of_term(ctx, a->p, v, n, &o)); return wrap(o); }
+  Poly taylor_polynomial_terms(const Poly& a, gfe::Var v, const std::vector<size_t>& orders) {
+    std::vector<uint64_t> os = u64(orders);
+    gtp_poly* o; check(gtp_taylor_polynomial_terms(ctx, a->p, v, os.data(), (int)os.size(), &o)); return wrap(o);
+  }
+  Poly subst_var(const Poly& a, gfe::Var v, const Poly& s) { gtp_poly* o; check(gtp_subst_var(ctx, a->p, v, s->p, &o)); return wrap(o); }
+  Poly truncate_to_degree_p1(const Poly& a, size_t d) { gtp_poly* o; check(gtp_truncate_to_degree_p1(ctx, a->p, d, &o)); return wrap(o); }
+  Poly remove_last_variable(const Poly& a) { gtp_poly* o; check(gtp_remove_last_variable(ctx, a->p, &o)); return wrap(o); }
+  Poly extend_to_dim(const Poly& a, size_t ndim, size_t d) { gtp_poly* o; check(gtp_extend_to_dim(ctx, a->p, ndim, d, &o)); return wrap(o); }
+  double constant_term(const Poly& a) { double x; check(gtp_constant_term(ctx, a->p, &x)); return x; }
+  std::vector<double> gather_axis(const Poly& a, gfe::Var v, size_t count) {
+    std::vector<double> out(count);
+    if (count) check(gtp_gather_axis(ctx, a->p, v, count, out.data()));
+    return out;
+  }
+  size_t num_vars(const Poly& a) { return (size_t)gtp_ndim(a->p); }
+  std::vector<uint64_t> array_shape(const Poly& a) {
+    std::vector<uint64_t> s((size_t)gtp_ndim(a->p) + 1);
+    gtp_shape(a->p, s.data());
+    s.resize((size_t)gtp_ndim(a->p));
+    return s;
+  }
+  std::optional<double> extract_constant(const Poly& a) {
+    int is_c = 0; double v = 0;
+    check(gtp_extract_constant(ctx, a->p, &is_c, &v));
+    if (is_c) return v;
+    return std::nullopt;
+  }
+  std::vector<double> to_host(const Poly& a) {
+    std::vector<double> out(gtp_len(a->p));
+    check(gtp_to_host(ctx, a->p, out.data()));
+    return out;
+  }
+};
+
+}  // namespace
+
+struct gtp_sgcl_result {
+  gfe::RunResult r;
+};
+
+extern "C" {
+
+int gtp_run_sgcl(gtp_ctx* ctx, const char* source, int64_t limit, int flags, uint64_t unroll, gtp_sgcl_result** out,
+                 char* err, size_t err_cap) {
+  if (!ctx || !source || !out) return GTP_ERR_ARG;
+  try {
+    GpuBackend backend{ctx};
+    gfe::RunOptions opt;
+    if (limit >= 0) opt.limit = (size_t)limit;
+    opt.no_probs = (flags & 1) != 0;
+    opt.no_simplify_gf = (flags & 2) != 0;
+    opt.bounds = (flags & 4) != 0;
+    opt.unroll = (size_t)unroll;
+    auto res = std::make_unique<gtp_sgcl_result>();
+    res->r = gfe::run_program(backend, source, opt);
+    *out = res.release();
+    return GTP_OK;
+  } catch (const std::exception& e) {
+    if (err && err_cap) {
+      std::strncpy(err, e.what(), err_cap - 1);
+      err[err_cap - 1] = '\0';
+    }
+    return GTP_ERR_INDEX;   // the reference panics on every error of this path (parse error, assert!)
+  }
+}
+void gtp_sgcl_free(gtp_sgcl_result* r) { delete r; }
+const char* gtp_sgcl_report(const gtp_sgcl_result* r) { return r->r.report.c_str(); }
+void gtp_sgcl_moments(const gtp_sgcl_result* r, double* out11) {
+  const gfe::RunResult& x = r->r;
+  const double v[11] = {x.total, x.mean, x.raw2, x.raw3, x.raw4, x.stddev, x.variance, x.central3, x.central4, x.skewness, x.kurtosis};
+  std::memcpy(out11, v, sizeof(v));
+}
+uint64_t gtp_sgcl_limit(const gtp_sgcl_result* r) { return r->r.probs.size(); }
+int gtp_sgcl_is_normalized(const gtp_sgcl_result* r) { return r->r.is_normalized ? 1 : 0; }
+void gtp_sgcl_probs(const gtp_sgcl_result* r, double* unnormalized, double* normalized) {
+  const gfe::RunResult& x = r->r;
+  for (size_t i = 0; i < x.probs.size(); i++) {
+    if (unnormalized) unnormalized[i] = x.probs[i];
+    if (normalized) normalized[i] = x.is_normalized ? x.probs[i] : x.normalized_probs[i];
+  }
+}
+void gtp_sgcl_stats(const gtp_sgcl_result* r, uint64_t* nodes_evaluated, uint64_t* cache_hits) {
+  if (nodes_evaluated) *nodes_evaluated = r->r.nodes_evaluated;
+  if (cache_hits) *cache_hits = r->r.cache_hits;
+}
+
+}  // extern "C"

@@ -308,15 +308,18 @@ __global__ void __launch_bounds__(SD_LANES) k_shift_down_tile(const double* __re
 #pragma unroll
     for (int l = 0; l < 4; l++) acc = __dadd_rn(acc, __dadd_rn(p[l], p[l + 4]));
     for (unsigned a = chunks * 8; a < head; a++) acc = __dadd_rn(acc, row[a]);
-    if (len <= n + 1) row[len - 1] = acc;                 // the single surviving slice
-    else row[n] = __dadd_rn(row[n], acc);
+    if (len <= n + 1) {                                   // the single surviving slice: coalesced direct store
+      out[lane0 + threadIdx.x] = acc;
+    } else {
+      row[n] = __dadd_rn(row[n], acc);
+    }
   }
+  if (len <= n + 1) return;
   __syncthreads();
-  const unsigned first = (len <= n + 1) ? len - 1 : n;
   double* dst = out + lane0 * out_len;
   for (unsigned e = threadIdx.x; e < lanes * out_len; e += SD_LANES) {
     unsigned o = e / out_len, k = e - o * out_len;
-    dst[e] = tile[o * pad + first + k];
+    dst[e] = tile[o * pad + n + k];
   }
 }
 

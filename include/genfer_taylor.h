@@ -177,6 +177,29 @@ int gtu_subst(gtp_ctx* ctx, const gtu_series* a, const gtu_series* subst, gtu_se
 int gtu_taylor_expansion_of_coeff(gtp_ctx* ctx, const gtu_series* a, uint64_t n, gtu_series** out); /* :69-89 */
 int gtu_eq(gtp_ctx* ctx, const gtu_series* a, const gtu_series* b, int* out);         /* derive(PartialEq) :8 */
 
+/* ---- host evaluator: an SGCL program end to end ------------------------------------ */
+/* Plays the role of the reference's `genfer file.sgcl` for the default f64 Taylor mode -- run() / run_program::<F64>
+ * (src/main.rs:108-227): parse (src/parser.rs), translate to a generating function (src/semantics/gf.rs), simplify
+ * and evaluate it (GenFun::simplify / eval, src/generating_function.rs:474-765), moments (moments_taylor :970-1005,
+ * limit 5) and probability masses (probs_taylor :937-967), post-processing and report (main.rs:301-473).  Every
+ * TaylorPoly operation of that pipeline is a gtp_* call on `ctx`, i.e. runs in the CUDA library.
+ *   limit  : --limit N, or -1 for the reference's automatic limit (finite support, else Markov's inequality)
+ *   flags  : 1 = --no-probs, 2 = --no-simplify-gf, 4 = print non-point intervals as [lo, hi] (--bounds style)
+ *   unroll : --unroll (reference default 8; only used by `while`)
+ * On error (parse error, or anything the reference would panic on) returns GTP_ERR_INDEX and copies the message
+ * into `err`.  The report is byte-compatible with the reference's stdout under --no-timing. */
+typedef struct gtp_sgcl_result gtp_sgcl_result;
+int gtp_run_sgcl(gtp_ctx* ctx, const char* source, int64_t limit, int flags, uint64_t unroll,
+                 gtp_sgcl_result** out, char* err, size_t err_cap);
+void gtp_sgcl_free(gtp_sgcl_result* r);
+const char* gtp_sgcl_report(const gtp_sgcl_result* r);
+/* Z, E, raw 2..4, sigma, V, central 3, central 4, skewness, kurtosis (the values the report prints) */
+void gtp_sgcl_moments(const gtp_sgcl_result* r, double* out11);
+uint64_t gtp_sgcl_limit(const gtp_sgcl_result* r);          /* number of probability masses computed */
+int gtp_sgcl_is_normalized(const gtp_sgcl_result* r);
+void gtp_sgcl_probs(const gtp_sgcl_result* r, double* unnormalized, double* normalized); /* p(i), p(i)/Z */
+void gtp_sgcl_stats(const gtp_sgcl_result* r, uint64_t* nodes_evaluated, uint64_t* cache_hits);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,7 +25,9 @@ UMAX = 2**64 - 1  # usize::MAX sentinel ("unbounded degree")
 
 def build(force: bool = False) -> str:
     """Compile liboracle.so with the committed Makefile (gcc, -ffp-contract=off)."""
-    srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "taylor_oracle.hpp", "Makefile")]
+    import glob
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "oracle_eval.cpp", "taylor_oracle.hpp", "Makefile")]
+    srcs += glob.glob(os.path.join(_HERE, "..", "genfer_b200", "csrc", "evaluator", "*.hpp"))
     if (not force and os.path.exists(_LIB_PATH)
             and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in srcs)):
         return _LIB_PATH
@@ -423,6 +425,47 @@ def mul_rows(x: np.ndarray, y: np.ndarray, rshape: Sequence[int], rows: Sequence
     macs = lib().orc_mul_rows(x.ndim, _u64(x.shape), _f64(x), _u64(y.shape), _f64(y), _u64(r.shape), _f64(r),
                               _u64(rows), len(rows))
     return r, macs
+
+
+class SgclResult:
+    """Outcome of running an SGCL program end to end (report = the reference's stdout with --no-timing)."""
+
+    def __init__(self, report, moments, probs, normalized_probs):
+        self.report = report
+        (self.total, self.mean, self.raw2, self.raw3, self.raw4, self.stddev, self.variance, self.central3,
+         self.central4, self.skewness, self.kurtosis) = moments
+        self.moments = list(moments)
+        self.probs = probs
+        self.normalized_probs = normalized_probs
+
+
+def run_sgcl(source: str, limit: Optional[int] = None, no_probs: bool = False, no_simplify_gf: bool = False,
+             unroll: int = 8) -> SgclResult:
+    """The host evaluator instantiated over the CPU oracle (oracle_eval.cpp): reference-order f64 arithmetic."""
+    L = lib()
+    L.orc_run_sgcl.argtypes = [C.c_char_p, C.c_int64, C.c_int, C.c_uint64, C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]
+    L.orc_sgcl_report.restype = C.c_char_p
+    L.orc_sgcl_report.argtypes = [C.c_void_p]
+    L.orc_sgcl_moments.argtypes = [C.c_void_p, _f64p]
+    L.orc_sgcl_limit.restype = C.c_uint64
+    L.orc_sgcl_limit.argtypes = [C.c_void_p]
+    L.orc_sgcl_probs.argtypes = [C.c_void_p, _f64p, _f64p]
+    L.orc_sgcl_free.argtypes = [C.c_void_p]
+    h = C.c_void_p()
+    err = C.create_string_buffer(2048)
+    flags = (1 if no_probs else 0) | (2 if no_simplify_gf else 0)
+    rc = L.orc_run_sgcl(source.encode(), -1 if limit is None else int(limit), flags, unroll, C.byref(h), err, 2048)
+    if rc != 0:
+        raise OracleError(err.value.decode())
+    try:
+        m = (C.c_double * 11)()
+        L.orc_sgcl_moments(h, m)
+        n = int(L.orc_sgcl_limit(h))
+        p, q = (C.c_double * max(n, 1))(), (C.c_double * max(n, 1))()
+        L.orc_sgcl_probs(h, p, q)
+        return SgclResult(L.orc_sgcl_report(h).decode(), list(m), list(p)[:n], list(q)[:n])
+    finally:
+        L.orc_sgcl_free(h)
 
 
 def mul_macs(xshape, yshape, rshape) -> float:

@@ -1,0 +1,114 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY.
+// The product's host evaluator (genfer_b200/csrc/evaluator/*.hpp: parser, GF translation, GenFun::eval, report --
+// all host control logic) instantiated over the CPU restatement of TaylorPoly<f64> (taylor_oracle.hpp) instead of
+// the CUDA library.  With the reference's operation order and separate multiply/add this reproduces the
+// reference's stdout byte for byte on its .expect fixtures (tests/test_oracle_sgcl.py), which pins both the
+// oracle's arithmetic and the shared host logic.  Never linked into or called from the product path.
+#include <cstring>
+#include <memory>
+
+#include "../genfer_b200/csrc/evaluator/report.hpp"
+#include "taylor_oracle.hpp"
+
+namespace {
+
+using TP = orc::TaylorPoly<double>;
+
+struct OracleBackend {
+  using Poly = std::shared_ptr<const TP>;
+  static Poly mk(TP t) { return std::make_shared<const TP>(std::move(t)); }
+  static std::vector<orc::usize> us(const std::vector<uint64_t>& v) {
+    std::vector<orc::usize> r;
+    for (uint64_t x : v) r.push_back(x == UINT64_MAX ? orc::UMAX : (orc::usize)x);
+    return r;
+  }
+  Poly from_scalar(double x) { return mk(TP::from_scalar(x)); }
+  Poly var(size_t v, double x, size_t len) { return mk(TP::var(v, x, len)); }
+  Poly var_at_zero(size_t v, size_t len) { return mk(TP::var_at_zero(v, len)); }
+  Poly var_with_degrees(size_t v, double x, const std::vector<uint64_t>& d) { return mk(TP::var_with_degrees_p1(v, x, us(d))); }
+  Poly zero_with(const std::vector<uint64_t>& d) { return mk(TP::zero_with(us(d))); }
+  Poly new_poly(const std::vector<uint64_t>& shape, const std::vector<uint64_t>& degrees, const double* data) {
+    orc::Arr<double> a(us(shape), 0.0);
+    for (size_t i = 0; i < a.data.size(); i++) a.data[i] = data[i];
+    return mk(TP(std::move(a), us(degrees)));
+  }
+  Poly add(const Poly& a, const Poly& b) { return mk(orc::tp_add(*a, *b)); }
+  Poly sub(const Poly& a, const Poly& b) { return mk(orc::tp_sub(*a, *b)); }
+  Poly mul(const Poly& a, const Poly& b) { return mk(orc::tp_mul(*a, *b)); }
+  Poly div(const Poly& a, const Poly& b) { return mk(orc::tp_div(*a, *b)); }
+  Poly neg(const Poly& a) { return mk(orc::tp_neg(*a)); }
+  Poly exp(const Poly& a) { return mk(a->exp()); }
+  Poly log(const Poly& a) { return mk(a->log()); }
+  Poly pow(const Poly& a, uint32_t e) { return mk(a->pow(e)); }
+  Poly derivative(const Poly& a, size_t v, size_t n) { return mk(a->derivative(v, n)); }
+  Poly taylor_expansion_of_coeff(const Poly& a, size_t v, size_t n) { return mk(a->taylor_expansion_of_coeff(v, n)); }
+  Poly shift_down(const Poly& a, size_t v, size_t n) { return mk(a->shift_down(v, n)); }
+  Poly coefficients_of_term(const Poly& a, size_t v, size_t n) { return mk(a->coefficients_of_term(v, n)); }
+  Poly taylor_polynomial_terms(const Poly& a, size_t v, const std::vector<size_t>& orders) {
+    return mk(a->taylor_polynomial_terms(v, std::vector<orc::usize>(orders.begin(), orders.end())));
+  }
+  Poly subst_var(const Poly& a, size_t v, const Poly& s) { return mk(a->subst_var(v, *s)); }
+  Poly truncate_to_degree_p1(const Poly& a, size_t d) { return mk(a->truncate_to_degree_p1(d)); }
+  Poly remove_last_variable(const Poly& a) { return mk(a->remove_last_variable()); }
+  Poly extend_to_dim(const Poly& a, size_t ndim, size_t d) { return mk(a->extend_to_dim(ndim, d)); }
+  double constant_term(const Poly& a) { return a->constant_term(); }
+  std::vector<double> gather_axis(const Poly& a, size_t v, size_t count) {   // `count` coefficient() calls (:959-965)
+    std::vector<double> out;
+    std::vector<orc::usize> idx(a->num_vars(), 0);
+    for (size_t i = 0; i < count; i++) {
+      idx.at(v) = i;
+      out.push_back(a->coefficient(idx));
+    }
+    return out;
+  }
+  size_t num_vars(const Poly& a) { return a->num_vars(); }
+  std::vector<uint64_t> array_shape(const Poly& a) { return std::vector<uint64_t>(a->coeffs.shape.begin(), a->coeffs.shape.end()); }
+  std::optional<double> extract_constant(const Poly& a) { return a->extract_constant(); }
+  std::vector<double> to_host(const Poly& a) { return a->coeffs.data; }
+};
+
+}  // namespace
+
+struct orc_sgcl_result {
+  gfe::RunResult r;
+};
+
+extern "C" {
+int orc_run_sgcl(const char* source, int64_t limit, int flags, uint64_t unroll, orc_sgcl_result** out, char* err, size_t err_cap) {
+  try {
+    OracleBackend backend;
+    gfe::RunOptions opt;
+    if (limit >= 0) opt.limit = (size_t)limit;
+    opt.no_probs = (flags & 1) != 0;
+    opt.no_simplify_gf = (flags & 2) != 0;
+    opt.bounds = (flags & 4) != 0;
+    opt.unroll = (size_t)unroll;
+    auto res = std::make_unique<orc_sgcl_result>();
+    res->r = gfe::run_program(backend, source, opt);
+    *out = res.release();
+    return 0;
+  } catch (const std::exception& e) {
+    if (err && err_cap) {
+      std::strncpy(err, e.what(), err_cap - 1);
+      err[err_cap - 1] = '\0';
+    }
+    return 1;
+  }
+}
+void orc_sgcl_free(orc_sgcl_result* r) { delete r; }
+const char* orc_sgcl_report(const orc_sgcl_result* r) { return r->r.report.c_str(); }
+void orc_sgcl_moments(const orc_sgcl_result* r, double* out11) {
+  const gfe::RunResult& x = r->r;
+  const double v[11] = {x.total, x.mean, x.raw2, x.raw3, x.raw4, x.stddev, x.variance, x.central3, x.central4, x.skewness, x.kurtosis};
+  std::memcpy(out11, v, sizeof(v));
+}
+void orc_sgcl_stats(const orc_sgcl_result* r, uint64_t* nodes, uint64_t* hits) { *nodes = r->r.nodes_evaluated; *hits = r->r.cache_hits; }
+uint64_t orc_sgcl_limit(const orc_sgcl_result* r) { return r->r.probs.size(); }
+void orc_sgcl_probs(const orc_sgcl_result* r, double* unnormalized, double* normalized) {
+  const gfe::RunResult& x = r->r;
+  for (size_t i = 0; i < x.probs.size(); i++) {
+    if (unnormalized) unnormalized[i] = x.probs[i];
+    if (normalized) normalized[i] = x.is_normalized ? x.probs[i] : x.normalized_probs[i];
+  }
+}
+}

@@ -1,0 +1,115 @@
+"""End-to-end parity on the GPU (BASELINE configs C1-C3, C5): gtp_run_sgcl -- the host evaluator with
+every TaylorPoly operation executed by the CUDA library -- against the reference's golden stdout and the oracle.
+
+Bar: the report is byte-identical to the reference's `.expect` wherever every kernel on the path is a bit-exact one;
+where the DFMA product or an N-D recurrence is involved, Z, the moments and p(n) agree with the oracle within
+1e-12 relative (north_star's tolerance), with an absolute floor of 1e-12 * Z for masses the reference prints as 0.
+"""
+import glob
+import os
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sgcl")
+RTOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import genfer_b200
+    c = genfer_b200.Context(0)
+    yield c
+    c.close()
+
+
+def fixtures():
+    return [os.path.relpath(s, GOLD) for s in sorted(glob.glob(os.path.join(GOLD, "*", "*.sgcl")))
+            if os.path.exists(s[:-5] + ".expect")]
+
+
+def close(a, b, floor):
+    return abs(a - b) <= RTOL * abs(b) + floor or (a != a and b != b)
+
+
+def compare_with_oracle(g, src, opts):
+    from oracle import oracle as O
+    o = O.run_sgcl(src, limit=opts["limit"], no_probs=opts["no_probs"], no_simplify_gf=opts["no_simplify_gf"],
+                   unroll=opts["unroll"])
+    # Z, E and the raw moments are direct read-outs; central / standardised moments are differences of those and
+    # amplify relative error by the cancellation factor, so they are checked at the scale of the raw moments
+    assert close(g.total, o.total, 0.0), (g.total, o.total)
+    raw_scale = [1.0, max(abs(o.mean), 1.0), max(abs(o.raw2), 1.0), max(abs(o.raw3), 1.0), max(abs(o.raw4), 1.0)]
+    for k, (a, b) in enumerate(zip(g.moments[:5], o.moments[:5])):
+        assert close(a, b, RTOL * raw_scale[k]), (k, a, b)
+    assert len(g.probs) == len(o.probs)
+    floor = RTOL * abs(o.total)
+    for i, (a, b) in enumerate(zip(g.probs, o.probs)):
+        assert close(a, b, floor), (i, a, b)
+    for i, (a, b) in enumerate(zip(g.normalized_probs, o.normalized_probs)):
+        assert close(a, b, RTOL), (i, a, b)
+
+
+@pytest.mark.parametrize("rel", fixtures())
+def test_gpu_matches_reference_golden(ctx, rel):
+    import genfer_b200
+    src = open(os.path.join(GOLD, rel)).read()
+    expect = open(os.path.join(GOLD, rel[:-5] + ".expect")).read()
+    opts = genfer_b200.parse_flags(src)
+    g = genfer_b200.run_sgcl(src, limit=opts["limit"], no_probs=opts["no_probs"], no_simplify_gf=opts["no_simplify_gf"],
+                             unroll=opts["unroll"], ctx=ctx)
+    if g.report != expect:
+        compare_with_oracle(g, src, opts)
+
+
+def test_gpu_golden_mostly_byte_identical(ctx):
+    """How many reports are byte-identical (documentation of the bit-exact share; must not regress below 90 %)."""
+    import genfer_b200
+    same = total = 0
+    for rel in fixtures():
+        if os.path.getsize(os.path.join(GOLD, rel)) > 50_000:
+            continue
+        src = open(os.path.join(GOLD, rel)).read()
+        expect = open(os.path.join(GOLD, rel[:-5] + ".expect")).read()
+        opts = genfer_b200.parse_flags(src)
+        g = genfer_b200.run_sgcl(src, limit=opts["limit"], no_probs=opts["no_probs"],
+                                 no_simplify_gf=opts["no_simplify_gf"], unroll=opts["unroll"], ctx=ctx)
+        total += 1
+        same += g.report == expect
+    print(f"byte-identical reports: {same}/{total}")
+    assert same >= 0.9 * total
+
+
+@pytest.mark.parametrize("prog", ["burglar_alarm", "max", "monty_hall", "monty_hall_nested", "grass", "fuzzy_or"])
+def test_gpu_prodigy_config_c5(ctx, prog):
+    """benchmarks/prodigy multi-variable programs (5-10 variables; finite supports -> compact tensors)."""
+    import genfer_b200
+    from oracle import oracle as O
+    src = open(os.path.join(GOLD, "config", prog + ".sgcl")).read()
+    g = genfer_b200.run_sgcl(src, ctx=ctx)
+    o = O.run_sgcl(src)
+    if g.report != o.report:
+        compare_with_oracle(g, src, genfer_b200.parse_flags(src))
+    if prog == "burglar_alarm":
+        assert abs(g.normalized_probs[1] - 2969983 / 992160802) <= 1e-14
+
+
+def test_gpu_example_config_c1(ctx):
+    import math
+    import genfer_b200
+    src = open(os.path.join(GOLD, "config", "example.sgcl")).read()
+    g = genfer_b200.run_sgcl(src, limit=25, ctx=ctx)
+    assert abs(g.total - 2 * math.exp(-2)) <= 1e-15
+    assert abs(g.mean - 9.0) <= 1e-12
+    for n, p in enumerate(g.probs):
+        exact = math.exp(-10) * 10.0 ** n / math.factorial(n) * n * 0.2 * 0.8 ** (n - 1) if n else 0.0
+        assert abs(p - exact) <= 1e-15 + 1e-12 * exact
+
+
+def test_parse_error_is_a_panic(ctx):
+    import genfer_b200
+    with pytest.raises(genfer_b200.TaylorPanic):
+        genfer_b200.run_sgcl("x ~ Poisson(;\nreturn x;", ctx=ctx)
+    with pytest.raises(genfer_b200.TaylorPanic):
+        genfer_b200.run_sgcl("x ~ Poisson(1);\nreturn y;", ctx=ctx)

@@ -1,0 +1,55 @@
+"""Pins the oracle end to end: the host evaluator over the CPU restatement reproduces the reference's stdout
+BYTE FOR BYTE on the reference's own golden files (tests/golden/sgcl/**, copied by make_sgcl_fixtures.py from
+test/expect/** and benchmarks/neurips2023/**; harness restated from tests/integration.rs:18-60).  CPU only."""
+import glob
+import os
+
+import pytest
+
+from genfer_b200.evaluator import parse_flags
+from oracle import oracle as O
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sgcl")
+SLOW = {"mixture"}   # 35 s on one CPU core: covered on the GPU, and here only with RUN_SLOW_TESTS=1
+
+
+def fixtures():
+    out = []
+    for src in sorted(glob.glob(os.path.join(GOLD, "*", "*.sgcl"))):
+        if os.path.exists(src[:-5] + ".expect"):
+            out.append(os.path.relpath(src, GOLD))
+    return out
+
+
+@pytest.mark.parametrize("rel", fixtures())
+def test_oracle_reproduces_reference_stdout(rel):
+    name = os.path.basename(rel)[:-5]
+    if name in SLOW and not os.environ.get("RUN_SLOW_TESTS"):
+        pytest.skip("slow on CPU")
+    src = open(os.path.join(GOLD, rel)).read()
+    expect = open(os.path.join(GOLD, rel[:-5] + ".expect")).read()
+    opts = parse_flags(src)
+    assert not opts["unsupported"]
+    got = O.run_sgcl(src, limit=opts["limit"], no_probs=opts["no_probs"], no_simplify_gf=opts["no_simplify_gf"],
+                     unroll=opts["unroll"])
+    assert got.report == expect
+
+
+def test_example_config_c1_closed_form():
+    """example.sgcl --limit 25 (BASELINE config C1): Z = 2 e^-2, E = 9, p(n) = e^-10 10^n/n! * n 0.2 0.8^(n-1)."""
+    import math
+    src = open(os.path.join(GOLD, "config", "example.sgcl")).read()
+    r = O.run_sgcl(src, limit=25)
+    assert abs(r.total - 2 * math.exp(-2)) <= 1e-15
+    assert abs(r.mean - 9.0) <= 1e-12
+    for n, p in enumerate(r.probs):
+        exact = math.exp(-10) * 10.0 ** n / math.factorial(n) * n * 0.2 * 0.8 ** (n - 1) if n else 0.0
+        assert abs(p - exact) <= 1e-15 + 1e-12 * exact
+
+
+def test_prodigy_burglar_alarm_exact_rational():
+    """benchmarks/prodigy/burglar_alarm.sgcl quotes Pr[burglary] = 2969983/992160802 in its `Original code` comment
+    (also benchmarks/neurips2023/exact/alarm/alarm.expected)."""
+    src = open(os.path.join(GOLD, "config", "burglar_alarm.sgcl")).read()
+    r = O.run_sgcl(src)
+    assert abs(r.normalized_probs[1] - 2969983 / 992160802) <= 1e-15

@@ -192,13 +192,15 @@ template <class K> int run(const char* name, K kern, double dfma_per_iter, int i
   return 0;
 }
 
-int main() {
+int main_lds(const double* src, double* sink);
+int main(int argc, char** argv) {
   double h[128];
   for (int i = 0; i < 128; i++) h[i] = 1.0 + 1e-3 * i;
   h[64] = 1.0000001; h[65] = 1e-9;
   double *src, *sink;
   CK(cudaMalloc(&src, sizeof(h))); CK(cudaMalloc(&sink, 64 * 8));
   CK(cudaMemcpy(src, h, sizeof(h), cudaMemcpyHostToDevice));
+  if (argc > 1) return main_lds(src, sink);
   for (int c : {2, 4}) {
     run("chain8 (a=fma(a,m,c))", p_chain8, 128, 8192, c, src, sink);
     run("two<16> (a=fma(b,m,a))", p_two<16>, 128, 8192, c, src, sink);
@@ -219,6 +221,197 @@ int main() {
     run("block1n<2>", p_block1n<2>, 272, 4096, c, src, sink);
     run("block1n<3>", p_block1n<3>, 408, 2048, c, src, sink);
     run("block1n<4>", p_block1n<4>, 544, 2048, c, src, sink);
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Patterns WITH their shared-memory operand loads (rows of 16 doubles, stride 18), one "item" per loop
+// iteration, rows rotating through a small slab so addresses are not loop-invariant.
+// ------------------------------------------------------------------------------------------------
+#define ROWS 64
+#define RS 18
+__device__ __forceinline__ void ld_row(double (&r)[16], const double* p) {
+#pragma unroll
+  for (int i = 0; i < 16; i += 2) { double2 v = *reinterpret_cast<const double2*>(p + i); r[i] = v.x; r[i + 1] = v.y; }
+}
+// current kernel body: 2 x rows, 2 y rows -> 3 z rows (x loaded progressively)
+__global__ void __launch_bounds__(128) p_lds_block22(int iters, const double* src, double* sink) {
+  extern __shared__ __align__(16) double sm[];
+  for (int i = threadIdx.x; i < ROWS * RS * 2; i += 128) sm[i] = src[i & 63];
+  __syncthreads();
+  double z0[16], z1[16], z2[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) z0[i] = z1[i] = z2[i] = 0.0;
+  unsigned r = threadIdx.x;
+  for (int it = 0; it < iters; it++) {
+    r = (r * 5 + 3) & (ROWS - 2);
+    const double* xs = sm + r * RS; const double* ys = sm + ROWS * RS + ((r + 6) & (ROWS - 2)) * RS;
+    double y0[16], y1[16];
+    ld_row(y0, ys); ld_row(y1, ys + RS);
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+      double2 xa = *reinterpret_cast<const double2*>(xs + j);
+      double2 xb = *reinterpret_cast<const double2*>(xs + RS + j);
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const double xaj = h ? xa.y : xa.x, xbj = h ? xb.y : xb.x;
+        const int jj = j + h;
+#pragma unroll
+        for (int kk = jj; kk < 16; kk++) {
+          z0[kk] = fma(xaj, y0[kk - jj], z0[kk]);
+          z1[kk] = fma(xaj, y1[kk - jj], z1[kk]);
+          z1[kk] = fma(xbj, y0[kk - jj], z1[kk]);
+          z2[kk] = fma(xbj, y1[kk - jj], z2[kk]);
+        }
+      }
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) s += z0[i] + z1[i] + z2[i];
+  if (s == 12345.678) sink[0] = s;
+}
+// same block, four separate accumulator rows (z1 split in two: no double update of one accumulator)
+__global__ void __launch_bounds__(128) p_lds_block22s(int iters, const double* src, double* sink) {
+  extern __shared__ __align__(16) double sm[];
+  for (int i = threadIdx.x; i < ROWS * RS * 2; i += 128) sm[i] = src[i & 63];
+  __syncthreads();
+  double z0[16], z1a[16], z1b[16], z2[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) z0[i] = z1a[i] = z1b[i] = z2[i] = 0.0;
+  unsigned r = threadIdx.x;
+  for (int it = 0; it < iters; it++) {
+    r = (r * 5 + 3) & (ROWS - 2);
+    const double* xs = sm + r * RS; const double* ys = sm + ROWS * RS + ((r + 6) & (ROWS - 2)) * RS;
+    double y0[16], y1[16];
+    ld_row(y0, ys); ld_row(y1, ys + RS);
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+      double2 xa = *reinterpret_cast<const double2*>(xs + j);
+      double2 xb = *reinterpret_cast<const double2*>(xs + RS + j);
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const double xaj = h ? xa.y : xa.x, xbj = h ? xb.y : xb.x;
+        const int jj = j + h;
+#pragma unroll
+        for (int kk = jj; kk < 16; kk++) {
+          z0[kk] = fma(xaj, y0[kk - jj], z0[kk]);
+          z1a[kk] = fma(xaj, y1[kk - jj], z1a[kk]);
+          z1b[kk] = fma(xbj, y0[kk - jj], z1b[kk]);
+          z2[kk] = fma(xbj, y1[kk - jj], z2[kk]);
+        }
+      }
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) s += z0[i] + z1a[i] + z1b[i] + z2[i];
+  if (s == 12345.678) sink[0] = s;
+}
+// sliding 1xN: per step ONE x row and ONE new y row; N z rows and N y rows stay in registers (ring unrolled by N)
+template <int N> __global__ void __launch_bounds__(128) p_lds_slide(int iters, const double* src, double* sink) {
+  extern __shared__ __align__(16) double sm[];
+  for (int i = threadIdx.x; i < ROWS * RS * 2; i += 128) sm[i] = src[i & 63];
+  __syncthreads();
+  double z[N][16], y[N][16];
+#pragma unroll
+  for (int b = 0; b < N; b++)
+#pragma unroll
+    for (int i = 0; i < 16; i++) { z[b][i] = 0.0; y[b][i] = src[(threadIdx.x + b + i) & 63]; }
+  unsigned r = threadIdx.x;
+  for (int it = 0; it < iters; it += N) {
+#pragma unroll
+    for (int ph = 0; ph < N; ph++) {
+      r = (r * 5 + 3) & (ROWS - 1);
+      const double* xs = sm + r * RS; const double* ys = sm + ROWS * RS + ((r + 7) & (ROWS - 1)) * RS;
+      ld_row(y[ph], ys);     // the new y row replaces the oldest one
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        double2 xv = *reinterpret_cast<const double2*>(xs + j);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const double xj = h ? xv.y : xv.x;
+          const int jj = j + h;
+#pragma unroll
+          for (int b = 0; b < N; b++)
+#pragma unroll
+            for (int kk = jj; kk < 16; kk++) z[b][kk] = fma(xj, y[(ph + N - b) % N][kk - jj], z[b][kk]);
+        }
+      }
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int b = 0; b < N; b++)
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += z[b][i];
+  if (s == 12345.678) sink[0] = s;
+}
+// 1x1 with loads (reference point)
+__global__ void __launch_bounds__(128) p_lds_rowconv(int iters, const double* src, double* sink) {
+  extern __shared__ __align__(16) double sm[];
+  for (int i = threadIdx.x; i < ROWS * RS * 2; i += 128) sm[i] = src[i & 63];
+  __syncthreads();
+  double z[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) z[i] = 0.0;
+  unsigned r = threadIdx.x;
+  for (int it = 0; it < iters; it++) {
+    r = (r * 5 + 3) & (ROWS - 1);
+    const double* xs = sm + r * RS; const double* ys = sm + ROWS * RS + ((r + 7) & (ROWS - 1)) * RS;
+    double y[16];
+    ld_row(y, ys);
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+      double2 xv = *reinterpret_cast<const double2*>(xs + j);
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const double xj = h ? xv.y : xv.x;
+        const int jj = j + h;
+#pragma unroll
+        for (int kk = jj; kk < 16; kk++) z[kk] = fma(xj, y[kk - jj], z[kk]);
+      }
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) s += z[i];
+  if (s == 12345.678) sink[0] = s;
+}
+
+template <class K> int run_lds(const char* name, K kern, double dfma_per_iter, int iters, int ctas_per_sm, const double* src, double* sink) {
+  int dev_sms = 148;
+  cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, 0);
+  int grid = dev_sms * ctas_per_sm;
+  size_t smem = (size_t)(220 * 1024 / ctas_per_sm) & ~(size_t)1023;   // pins the occupancy
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; rep++) {
+    CK(cudaEventRecord(e0));
+    kern<<<grid, 128, smem>>>(iters, src, sink);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  CK(cudaGetLastError());
+  cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, kern);
+  double fl = (double)grid * 128 * iters * dfma_per_iter * 2.0;
+  printf("LDS %-24s ctas/sm %d regs %3d  %7.2f TF/s  %8.3f ms\n", name, ctas_per_sm, fa.numRegs, fl / (best * 1e-3) / 1e12, best);
+  return 0;
+}
+
+int main_lds(const double* src, double* sink) {
+  for (int c : {2, 3, 4}) {
+    run_lds("rowconv 1x1", p_lds_rowconv, 136, 6144, c, src, sink);
+    run_lds("block22", p_lds_block22, 544, 1536, c, src, sink);
+    run_lds("block22 split z1", p_lds_block22s, 544, 1536, c, src, sink);
+    run_lds("slide<2>", p_lds_slide<2>, 272, 3072, c, src, sink);
+    run_lds("slide<3>", p_lds_slide<3>, 408, 2048 + 1, c, src, sink);
+    run_lds("slide<4>", p_lds_slide<4>, 544, 1536, c, src, sink);
   }
   return 0;
 }
