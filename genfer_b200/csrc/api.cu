@@ -101,16 +101,20 @@ PolyP zero_with(Ctx& c, const Shape& degrees) {  // :208-216
 void classify(Ctx& c, const gtp_poly& p) {
   if (p.cls->known) return;
   if (p.len() == 1) {
-    GTP_CUDA(cudaMemcpyAsync(&c.rb_host->vals[0], p.ptr(), sizeof(double), cudaMemcpyDeviceToHost, c.stream));
-    c.sync();
+    if (!classify_small_zero_copy(c, p.ptr(), p.shape)) {
+      GTP_CUDA(cudaMemcpyAsync(&c.rb_host->vals[0], p.ptr(), sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+      c.sync();
+    }
     p.cls->first = c.rb_host->vals[0];
     p.cls->linear = false;
     p.cls->known = true;
     return;
   }
-  launch_classify(c, p.ptr(), p.shape, c.rb_dev);
-  GTP_CUDA(cudaMemcpyAsync(c.rb_host, c.rb_dev, sizeof(Readback), cudaMemcpyDeviceToHost, c.stream));
-  c.sync();
+  if (!classify_small_zero_copy(c, p.ptr(), p.shape)) {
+    launch_classify(c, p.ptr(), p.shape, c.rb_dev);
+    GTP_CUDA(cudaMemcpyAsync(c.rb_host, c.rb_dev, offsetof(Readback, seq), cudaMemcpyDeviceToHost, c.stream));
+    c.sync();
+  }
   p.cls->first = c.rb_host->vals[0];
   p.cls->linear = false;
   for (size_t v = 0; v < p.shape.size(); v++) {  // first axis of stored length >= 2 that qualifies (:277-292)
@@ -644,7 +648,12 @@ int gtp_ctx_create(int device, void* cuda_stream, gtp_ctx** out) {
     GTP_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t thr = UINT64_MAX;
     GTP_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
-    GTP_CUDA(cudaMallocHost((void**)&c->rb_host, sizeof(Readback)));
+    GTP_CUDA(cudaHostAlloc((void**)&c->rb_host, sizeof(Readback), cudaHostAllocMapped | cudaHostAllocPortable));
+    memset(c->rb_host, 0, sizeof(Readback));
+    if (cudaHostGetDevicePointer((void**)&c->rb_host_dev, c->rb_host, 0) != cudaSuccess) {
+      c->rb_host_dev = nullptr;   // no zero-copy: classify() falls back to the copy + synchronise path
+      cudaGetLastError();
+    }
     GTP_CUDA(cudaMalloc((void**)&c->rb_dev, sizeof(Readback)));
     GTP_CUDA(cudaMemset(c->rb_dev, 0, sizeof(Readback)));
   });
@@ -899,6 +908,11 @@ int gtp_extend(gtp_ctx* c, const gtp_poly* a, int ndim, const uint64_t* new_size
 
 int gtp_constant_term(gtp_ctx* c, const gtp_poly* a, double* out) {  // :296-299
   return wrap(c, [&] {
+    if (a->len() <= 8192) {   // small: classification (cached per handle) already carries coeffs.first()
+      classify(*c, *a);
+      *out = a->cls->first;
+      return;
+    }
     GTP_CUDA(cudaMemcpyAsync(&c->rb_host->vals[0], a->ptr(), sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     c->sync();
     *out = c->rb_host->vals[0];

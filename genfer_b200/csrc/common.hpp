@@ -71,6 +71,7 @@ struct Readback {
   unsigned int viol_mask;  // classify: bit v set <=> axis v is NOT a linear axis
   unsigned int flag;       // generic boolean result (eq / any)
   double vals[64];         // c, m, sums, gathered scalars ...
+  volatile unsigned long long seq;  // written LAST by the single-CTA classify kernel (zero-copy path): host spins on it
 };
 
 struct Ctx {
@@ -85,6 +86,8 @@ struct Ctx {
   double* gather_host = nullptr;        // pinned, for gtp_gather_axis / to_host staging
   u64 gather_cap = 0;
   u64 launches = 0;
+  u64 rb_seq = 0;               // sequence number of the last zero-copy read-back request
+  Readback* rb_host_dev = nullptr;  // device alias of rb_host (mapped pinned memory)
   int fast_mul = 1;  // 0: reference-order kernel only, 1: auto, 2: force the blocked kernel even on tiny products (tests)
   std::shared_ptr<void> blk_plans;   // per-context cache of product plans (kernels_mul_blk.cu)
   bool blk_octet = false;            // experimental octet tables for single-plane slabs (8 staged pairs = 8 lanes)

@@ -72,6 +72,10 @@ void launch_shift_down(Ctx& ctx, const double* in, double* out, u64 outer, u64 l
 void launch_sum_all(Ctx& ctx, const double* in, u64 n, double* out_dev);
 // classification for extract_linear (:275-294): writes Readback{viol_mask, vals[0]=first} to rb_dev
 void launch_classify(Ctx& ctx, const double* in, const Shape& shape, Readback* rb_dev);
+// Small tensors (<= 8192 coefficients): ONE single-CTA kernel that writes the classification straight into the mapped
+// pinned page and bumps its sequence number; the host spins on it (no memset, no D2H copy, no stream synchronise).
+// Returns false if the tensor is too large for this path.
+bool classify_small_zero_copy(Ctx& ctx, const double* in, const Shape& shape);
 // rb_dev->flag = 1 iff every element compares == (IEEE)
 void launch_eq(Ctx& ctx, const double* a, const double* b, u64 n, Readback* rb_dev);
 // out[i] = i < len ? in[i*stride] : 0   for i < count

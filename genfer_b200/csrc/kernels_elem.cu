@@ -1,6 +1,8 @@
 // Element-wise, gather, shift and axis-reduction kernels (HBM-bound family, SURVEY 8a rows a3-a6,
 // a8, a13-a16, a18).  All arithmetic is plain IEEE double with explicit __dmul_rn/__dadd_rn where
 // the reference does a separate multiply and add, so these paths are bit-identical to the oracle.
+#include <atomic>
+
 #include "kernels.cuh"
 
 namespace gtp {
@@ -451,6 +453,74 @@ void launch_classify(Ctx& ctx, const double* in, const Shape& shape, Readback* r
   GTP_CUDA(cudaMemsetAsync(&rb_dev->viol_mask, 0, sizeof(unsigned), ctx.stream));
   int grid = (int)std::max<u64>(1, std::min<u64>((p.total + 255) / 256, (u64)ctx.sm_count * 4));
   GTP_LAUNCH(ctx, k_classify, grid, 256, 0, in, p, rb_dev);
+}
+
+__global__ void __launch_bounds__(256) k_classify_small(const double* __restrict__ in, const ClsParams p, Readback* rb,
+                                                        unsigned long long seq) {
+  __shared__ unsigned sh_mask;
+  if (threadIdx.x == 0) sh_mask = 0;
+  __syncthreads();
+  unsigned mask = 0;
+  for (u64 lin = threadIdx.x; lin < p.total; lin += blockDim.x) {
+    double x = in[lin];
+    if (x != 0.0) {
+      u64 rem = lin;
+      int nz_axis = -1, nz_count = 0;
+      unsigned nz_val = 0;
+      for (int d = p.ndim - 1; d >= 0; --d) {
+        unsigned i = (unsigned)(rem % p.shape[d]);
+        rem /= p.shape[d];
+        if (i != 0) {
+          nz_count++;
+          nz_axis = d;
+          nz_val = i;
+        }
+      }
+      if (nz_count >= 2) mask |= p.all_mask;
+      else if (nz_count == 1) mask |= (nz_val >= 2) ? p.all_mask : (p.all_mask & ~(1u << nz_axis));
+    }
+  }
+  if (mask) atomicOr(&sh_mask, mask);
+  __syncthreads();
+  if (threadIdx.x < p.ndim) rb->vals[1 + threadIdx.x] = p.shape[threadIdx.x] >= 2 ? in[p.str[threadIdx.x]] : 0.0;
+  if (threadIdx.x == 0) {
+    rb->vals[0] = in[0];
+    rb->viol_mask = sh_mask;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) rb->seq = seq;   // published last
+}
+
+bool classify_small_zero_copy(Ctx& ctx, const double* in, const Shape& shape) {
+  const u64 total = prod(shape);
+  if (total > 8192 || !ctx.rb_host_dev || shape.size() > (size_t)MAXD) return false;
+  ClsParams p;
+  memset(&p, 0, sizeof(p));
+  p.ndim = (int)shape.size();
+  p.total = total;
+  for (int d = 0; d < p.ndim; d++) p.shape[d] = (unsigned)shape[d];
+  long long st = 1;
+  for (int d = p.ndim - 1; d >= 0; --d) {
+    p.str[d] = st;
+    st *= (long long)shape[d];
+  }
+  p.all_mask = p.ndim >= 32 ? 0xffffffffu : ((1u << p.ndim) - 1u);
+  const unsigned long long seq = ++ctx.rb_seq;
+  GTP_LAUNCH(ctx, k_classify_small, 1, 256, 0, in, p, ctx.rb_host_dev, seq);
+  // spin on the mapped page; fall back to a stream query now and then so a failed launch cannot hang the host
+  for (unsigned long long spins = 0; ctx.rb_host->seq != seq; ++spins) {
+    if ((spins & 0xfffff) == 0xfffff) {
+      cudaError_t e = cudaStreamQuery(ctx.stream);
+      if (e != cudaSuccess && e != cudaErrorNotReady) GTP_CUDA(e);
+      if (e == cudaSuccess && ctx.rb_host->seq != seq) {   // stream drained but nothing published: treat as an error
+        GTP_CUDA(cudaStreamSynchronize(ctx.stream));
+        if (ctx.rb_host->seq != seq) throw Error(GTP_ERR_CUDA, "classification read-back was not published");
+      }
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);   // the payload is read only after its sequence number
+  return true;
 }
 
 __global__ void __launch_bounds__(256) k_eq(const double* __restrict__ a, const double* __restrict__ b, u64 n, Readback* rb) {
