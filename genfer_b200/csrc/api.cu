@@ -684,6 +684,7 @@ int gtp_ctx_set_fast_mul(gtp_ctx* c, int enabled) {
   // bit 2 (value 4) switches the blocked kernel's structured item tables off (A/B measurements)
   c->blk_fold_tables = (enabled & 4) == 0;
   c->blk_octet = (enabled & 8) != 0;   // experimental
+  c->use_slide = (enabled & 16) == 0;
   enabled &= 3;
   c->fast_mul = enabled < 0 ? 0 : (enabled > 2 ? 2 : enabled);
   return GTP_OK;

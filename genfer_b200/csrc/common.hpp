@@ -90,6 +90,8 @@ struct Ctx {
   Readback* rb_host_dev = nullptr;  // device alias of rb_host (mapped pinned memory)
   int fast_mul = 1;  // 0: reference-order kernel only, 1: auto, 2: force the blocked kernel even on tiny products (tests)
   std::shared_ptr<void> blk_plans;   // per-context cache of product plans (kernels_mul_blk.cu)
+  std::shared_ptr<void> slide_plans; // same for kernels_mul_slide.cu
+  bool use_slide = true;             // sliding 1x2 kernel for dense cube slabs (false: 2x2-blocked kernel everywhere)
   bool blk_octet = false;            // experimental octet tables for single-plane slabs (8 staged pairs = 8 lanes)
   bool blk_fold_tables = true;       // structured (folded) item tables for dense cube slabs; false: evenly dealt
 

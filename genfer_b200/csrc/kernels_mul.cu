@@ -107,15 +107,19 @@ double mul_macs(const Shape& xs, const Shape& ys, const Shape& rs) {
   return total;
 }
 
-// implemented in kernels_mul_blk.cu
+// implemented in kernels_mul_blk.cu / kernels_mul_slide.cu
 bool blk_mul_applicable(const Ctx& ctx, const MulArgs& a);
 void launch_mul_blk(Ctx& ctx, const MulArgs& a);
+bool slide_mul_applicable(const Ctx& ctx, const MulArgs& a);
+void launch_mul_slide(Ctx& ctx, const MulArgs& a);
 
-// 0: reference-order kernel, 2: 2x2-blocked DFMA kernel (kernels_mul_blk.cu).  (1 was the cube-16-only kernel of
+// 0: reference-order kernel, 2: 2x2-blocked DFMA kernel (kernels_mul_blk.cu), 3: sliding 1x2 DFMA kernel for dense
+// cube slabs (kernels_mul_slide.cu).  (1 was the cube-16-only kernel of
 // the first round; the blocked kernel with folded tables superseded it.)
 int mul_kernel_kind(const Ctx& ctx, const MulArgs& a) {
   if (!ctx.fast_mul) return 0;
   if ((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.y)) & 15u) return 0;  // cp.async 16-byte staging
+  if (ctx.use_slide && slide_mul_applicable(ctx, a)) return 3;
   return blk_mul_applicable(ctx, a) ? 2 : 0;
 }
 
@@ -183,6 +187,10 @@ void launch_mul(Ctx& ctx, const MulArgs& a_in) {
   const int kind = mul_kernel_kind(ctx, a);
   if (kind == 2) {
     launch_mul_blk(ctx, a);
+    return;
+  }
+  if (kind == 3) {
+    launch_mul_slide(ctx, a);
     return;
   }
   if (a.rows.empty()) {

@@ -25,7 +25,7 @@ fn main() {
             .flag("-std=c++17")
             .opt_level(3)
             .include(root.join("include"));
-        for f in ["api.cu", "api_uni.cu", "kernels_elem.cu", "kernels_mul.cu", "kernels_mul_blk.cu", "kernels_rec.cu", "univariate.cu"] {
+        for f in ["api.cu", "api_uni.cu", "kernels_elem.cu", "kernels_mul.cu", "kernels_mul_blk.cu", "kernels_mul_slide.cu", "kernels_rec.cu", "univariate.cu"] {
             let p = csrc.join(f);
             println!("cargo:rerun-if-changed={}", p.display());
             b.file(p);

@@ -82,14 +82,25 @@ BLK_CUBES = [(4, 8), (4, 10), (4, 12), (4, 14), (4, 16), (3, 32), (3, 24), (4, 2
 
 
 @pytest.mark.parametrize("n,d", BLK_CUBES)
-def test_blocked_kernel_cubes_match_oracle(ctx, n, d):
-    """The generic 2x2-blocked kernel (mode 2 forces it): every chunk length 8..16, chunked last axes
-    (20 = 2x10, 24 = 2x12, 28 = 2x14, 32 = 2x16, 48 = 3x16), folded and unfolded b1."""
+@pytest.mark.parametrize("mode", [2, 18])
+def test_blocked_kernel_cubes_match_oracle(ctx, n, d, mode):
+    """The DFMA kernels on small cubes (mode 2 forces them; +16 switches the sliding 1x2 kernel off so the 2x2-blocked
+    one runs everywhere): every chunk length 8..16, chunked last axes (20 = 2x10, 24 = 2x12, 28 = 2x14, 32 = 2x16,
+    48 = 3x16), folded and unfolded b1."""
     from oracle import oracle as O
     x, y = synth_pgf((d,) * n, 20230517), synth_uniform((d,) * n, 20231210)
     ref = O.mul_raw(x, y, (d,) * n)
-    got = gpu_mul_raw(ctx, x, y, (d,) * n, fast=2)
+    got = gpu_mul_raw(ctx, x, y, (d,) * n, fast=mode)
     assert rel_err(got, ref) <= RTOL, rel_err(got, ref)
+
+
+@pytest.mark.parametrize("n,d", [(4, 12), (4, 16), (5, 12), (5, 16), (4, 8)])
+def test_kernel_selection(ctx, n, d):
+    """Dense cube slabs with >= 16 folded lanes take the sliding kernel (3), the rest the blocked one (2)."""
+    ctx.set_fast_mul(2)
+    kind = ctx.mul_kernel_kind((d,) * n, (d,) * n, (d,) * n)
+    ctx.set_fast_mul(1)
+    assert kind == (2 if d == 8 else 3)
 
 
 BLK_RAGGED = [((5, 7, 9, 16), (6, 4, 9, 16), (8, 9, 12, 16)), ((3, 5, 16), (4, 2, 16), (6, 6, 16)),
