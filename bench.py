@@ -315,7 +315,7 @@ def run_ours(args):
             traffic = json.load(open(tpath)).get(args.workload, {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "fp64", "kernel": "k_mul_blk" if kind == 2 else "k_mul_ordered",
+    roofline = {"bound": "fp64", "kernel": {2: "k_mul_blk", 3: "k_mul_slide"}.get(kind, "k_mul_ordered"),
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "FP64 FMA pipe measured live by gtp_fp64_peak_probe (8 independent DFMA chains/thread, all SMs); "

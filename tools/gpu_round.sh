@@ -10,6 +10,6 @@ cat $out/bench.json
 timeout 300 python tools/time_mul.py 4x32 5x16 6x12 5x24 6x16 > $out/sweep.jsonl 2>&1; cat $out/sweep.jsonl
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $out/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu > $out/bench_under_ncu.log 2>&1; echo "ncu list rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_mul_blk -s 1 -c 1 -o $out/prof_product \
+timeout 600 ncu --set full --clock-control none --import-source on -k 'regex:k_mul_(blk|slide)' -s 1 -c 1 -o $out/prof_product \
     python bench.py --steps 1 --warmup 1 --no-cpu --no-aux > $out/ncu_full.log 2>&1; echo "ncu full rc=$?"
 ls -la $out
