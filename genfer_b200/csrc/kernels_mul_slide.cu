@@ -21,7 +21,7 @@
 
 namespace gtp {
 
-constexpr int ST = 128;
+constexpr int ST = 128;   // maximum (and untiled) CTA size; tiled plans may launch fewer threads
 constexpr int S_MAXA = 6;
 
 struct SlideP {
@@ -37,7 +37,9 @@ struct SlideP {
   unsigned z_rows, z_up;          // rows per output slab; rows between (s) and (s+1)
   int G;
   int nsteps_lo, nsteps;          // both even
-  const uint2* table;             // [nsteps][ST]
+  int tiled;                      // 1: the plane axis is tiled (last A axis = tile index); units on the last tile
+                                  // sum skip the SE_UPPER steps (output planes beyond the truncation)
+  const uint2* table;             // [nsteps][blockDim.x]
   const uint4* units;
   const double* x;
   const double* y;
@@ -48,6 +50,7 @@ struct SlideP {
 constexpr unsigned SE_VALID = 1u << 31;
 constexpr unsigned SE_RELOAD = 1u << 26;
 constexpr unsigned SE_Z1 = 1u << 25;
+constexpr unsigned SE_UPPER = 1u << 27;   // tiled planes: the step feeds an output plane of the NEXT plane tile
 
 __device__ __forceinline__ void sl_cp16(void* smem, const void* gmem) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -101,12 +104,14 @@ __global__ void __launch_bounds__(ST, 3) k_mul_slide(const SlideP p) {
   double* Xs = smem;
   double* Ys = smem + (size_t)p.G * p.x_slab_sm;
   const int tid = threadIdx.x;
+  const int ST = blockDim.x;
   const uint4 unit = p.units[blockIdx.x];
   {  // zero fill once: the leading / trailing zero rows of the y planes are never overwritten
     const int total = p.G * (int)(p.x_slab_sm + p.y_slab_sm);
     for (int i = tid * 2; i < total; i += ST * 2) *reinterpret_cast<double2*>(smem + i) = make_double2(0.0, 0.0);
   }
   unsigned k[S_MAXA], lo[S_MAXA], ext[S_MAXA];
+  unsigned skip_mask = 0u;   // steps with any of these bits set are skipped
   {
     unsigned rem = unit.x;
 #pragma unroll
@@ -120,6 +125,7 @@ __global__ void __launch_bounds__(ST, 3) k_mul_slide(const SlideP p) {
         unsigned h = (k[a] + 1 < p.xa[a]) ? k[a] + 1 : p.xa[a];
         lo[a] = l;
         ext[a] = h > l ? h - l : 0;
+        if (p.tiled && a == p.na - 1 && k[a] + 1 == p.ra[a]) skip_mask = SE_UPPER;   // last plane tile: no next tile
       } else {
         k[a] = lo[a] = 0;
         ext[a] = 1;
@@ -173,7 +179,7 @@ __global__ void __launch_bounds__(ST, 3) k_mul_slide(const SlideP p) {
 #pragma unroll
         for (int par = 0; par < 2; par++) {
           const uint2 e = par ? e1 : e0;
-          if ((e.x & SE_VALID) && (int)((e.x >> 20) & 15u) < ng) {
+          if ((e.x & SE_VALID) && !(e.x & skip_mask) && (int)((e.x >> 20) & 15u) < ng) {
             const unsigned zkey = ((e.y >> 20) << 1) | ((e.x >> 25) & 1u);
             if (zkey != cur) {
               if (cur != 0xffffffffu) {
@@ -213,11 +219,14 @@ __global__ void __launch_bounds__(ST, 3) k_mul_slide(const SlideP p) {
 // host side
 // ------------------------------------------------------------------------------------------
 struct SlideGeom {
-  int nd, na;
+  int nd, na;      // na = real A axes (nd - 3); a tiled plan appends the plane-tile axis as one more A axis
   u64 lt, lc, D1, D2;
+  u64 T1, nt;      // planes per staged slab and number of plane tiles (T1 == D1, nt == 1: untiled)
+  int E;           // tiled: plane pairs of a class are interleaved over E lockstep lanes (T1 * E == 8)
+  int threads;     // CTA size
   u64 row, xplane, yplane, xslab, yslab, yfirst;
   int G;
-  int ctas;       // resident CTAs per SM the shared-memory footprint allows (3 or 2)
+  int ctas;       // resident CTAs per SM the shared-memory footprint allows
   size_t smem;
 };
 
@@ -232,7 +241,16 @@ static u64 odd_groups(u64 doubles) {   // round up to an even number of doubles 
   return doubles;
 }
 
-static bool slide_geom(const MulArgs& a, SlideGeom* g) {
+static void slide_smem_layout(SlideGeom* g) {
+  g->row = g->lt;                                         // lockstep lanes differ by plane, not by row: no row padding
+  g->xplane = odd_groups(g->D2 * g->lc * g->row);
+  g->yplane = odd_groups((g->D2 + 2) * g->lc * g->row);   // zero rows -1 and D2
+  g->yfirst = g->lc * g->row;
+  g->xslab = odd_groups(g->T1 * g->xplane);
+  g->yslab = odd_groups(g->T1 * g->yplane);
+}
+
+static bool slide_geom(const Ctx& ctx, const MulArgs& a, SlideGeom* g) {
   const int nd = a.ndim;
   if (nd < 4 || a.accumulate) return false;
   const u64 ltt = a.rs[nd - 1], D1 = a.rs[nd - 3], D2 = a.rs[nd - 2];
@@ -250,29 +268,55 @@ static bool slide_geom(const MulArgs& a, SlideGeom* g) {
   g->lc = ltt / lt;
   g->D1 = D1;
   g->D2 = D2;
-  const u64 lanes = (D1 / 2) * (D2 / 4);
-  if (lanes > (u64)ST || lanes < 16) return false;
-  if (D1 * D2 * g->lc >= 4096) return false;
-  g->row = lt;                                            // lockstep lanes differ by plane, not by row: no row padding
-  g->xplane = odd_groups(D2 * g->lc * g->row);
-  g->yplane = odd_groups((D2 + 2) * g->lc * g->row);      // zero rows -1 and D2
-  g->yfirst = g->lc * g->row;
-  g->xslab = odd_groups(D1 * g->xplane);
-  g->yslab = odd_groups(D1 * g->yplane);
-  const u64 pair = (g->xslab + g->yslab) * 8;
   const u64 budget3 = 74 * 1024, budget2 = 112 * 1024;
-  if (pair <= budget3) { g->ctas = 3; g->G = (int)std::min<u64>(8, budget3 / pair); }
-  else if (pair <= budget2) { g->ctas = 2; g->G = 1; }
-  else return false;
-  if (g->G * std::max(g->xslab, g->yslab) >= (1u << 20)) return false;
-  g->smem = (size_t)g->G * pair;
-  return true;
+  // ---- untiled: the whole (D1, D2, L) slab of each operand is staged ----
+  const u64 lanes = (D1 / 2) * (D2 / 4);
+  if (ctx.slide_tile == 0 && lanes <= (u64)ST && lanes >= 16 && D1 * D2 * g->lc < 4096) {
+    g->T1 = D1;
+    g->nt = 1;
+    g->E = 1;
+    g->threads = ST;
+    slide_smem_layout(g);
+    const u64 pair = (g->xslab + g->yslab) * 8;
+    bool ok = true;
+    if (pair <= budget3) { g->ctas = 3; g->G = (int)std::min<u64>(8, budget3 / pair); }
+    else if (pair <= budget2) { g->ctas = 2; g->G = 1; }
+    else ok = false;
+    if (ok && g->G * std::max(g->xslab, g->yslab) < (1u << 20)) {
+      g->smem = (size_t)g->G * pair;
+      return true;
+    }
+  }
+  // ---- tiled plane axis: slabs of T1 planes, one more A axis over the D1 / T1 tiles ----
+  if (g->na + 1 > S_MAXA) return false;
+  for (u64 T1 : {4, 8}) {
+    if (ctx.slide_tile != 0 && (u64)ctx.slide_tile != T1) continue;
+    if (D1 % T1 != 0 || D1 / T1 < 2) continue;
+    const u64 DD = D2 / 4, nl = 8 * DD;
+    if (nl > (u64)ST) continue;
+    if (2 * T1 * D2 * g->lc >= 4096) continue;
+    g->T1 = T1;
+    g->nt = D1 / T1;
+    g->E = (int)(8 / T1);
+    g->threads = (int)(nl * ((u64)ST / nl));
+    g->G = 1;
+    slide_smem_layout(g);
+    const u64 pair = (g->xslab + g->yslab) * 8;
+    if (pair > budget2 || std::max(g->xslab, g->yslab) >= (1u << 20)) continue;
+    // 170 registers x 384 threads fill the register file: at most 384 / threads CTAs
+    const u64 by_regs = std::max<u64>(1, 384 / (u64)((g->threads + 31) / 32 * 32));
+    const u64 by_smem = (227 * 1024) / (pair + 1024);
+    g->ctas = (int)std::max<u64>(1, std::min(by_regs, by_smem));
+    g->smem = (size_t)pair;
+    return true;
+  }
+  return false;
 }
 
 bool slide_mul_applicable(const Ctx& ctx, const MulArgs& a) {
   SlideGeom g;
-  if (!slide_geom(a, &g)) return false;
-  u64 slabs = a.row_count;
+  if (!slide_geom(ctx, a, &g)) return false;
+  u64 slabs = a.row_count * g.nt;
   for (int d = 1; d < g.na; d++) slabs *= a.rs[d];
   return slabs >= 64 || (ctx.fast_mul == 2 && slabs >= 1);
 }
@@ -342,6 +386,76 @@ static void build_slide_table(const SlideGeom& g, std::vector<uint2>* table, int
     }
 }
 
+// Tiled plane axis (see slide_geom): a slab holds T1 planes of tile tp of X and of tile tq of Y; their plane pairs
+// (j1, m1) feed the output planes r1 = j1 + m1 in 0 .. 2 T1 - 2 of output tile tp + tq (r1 >= T1: the next tile, SE_UPPER).
+// Class c owns the output planes {c, c + T1}: exactly T1 plane pairs (j1 = t, m1 = (c - t) mod T1, t = 0 .. T1-1), which
+// are dealt round-robin to E lockstep lanes (t = u E + tau).  The 8 lanes (c, tau) of a quarter-warp execute the same
+// (row pair, chunk, step) on different planes: x rows are broadcast per tau, y rows sit in T1 different planes =>
+// conflict-free LDS.128 (plane strides are odd numbers of 16-byte groups).  Lane d of the row-pair fold as untiled.
+static void build_slide_table_tiled(const SlideGeom& g, std::vector<uint2>* table, int* n_lo, int* n_hi) {
+  const int T1 = (int)g.T1, E = g.E, D2 = (int)g.D2, P = D2 / 2, DD = P / 2, LC = (int)g.lc;
+  const int nl = 8 * DD, NT = g.threads, T = NT / nl, U = T1 / E;
+  struct Step { unsigned xoff, yoff, zrow, z1ok, upper; bool run_start; };
+  std::vector<std::vector<Step>> seq_lo(nl), seq_hi(nl);
+  for (int d = 0; d < DD; d++)
+    for (int tau = 0; tau < E; tau++)
+      for (int c = 0; c < T1; c++) {
+        const int lane = d * 8 + tau * T1 + c;
+        int seam = 0;
+        for (int phase = 0; phase < 2; phase++) {
+          const int half = phase == 0 ? d : P - 1 - d;
+          const int s = 2 * half;
+          for (int kc = 0; kc < LC; kc++, seam++)
+            for (int uu = 0; uu < U; uu++) {
+              const int u = (seam & 1) ? U - 1 - uu : uu;
+              const int t = u * E + tau;
+              const int r1 = t <= c ? c : c + T1;
+              const int j1 = t, m1 = r1 - j1;
+              for (int jc = 0; jc < LC; jc++)
+                for (int mc = 0; mc < LC; mc++) {
+                  int kind;
+                  if (jc + mc == kc) kind = 0;
+                  else if (jc + mc + 1 == kc) kind = 1;
+                  else continue;
+                  const int a_hi = std::min(D2 - 1, s + 1);
+                  for (int a = 0; a <= a_hi; a++) {
+                    const int m2 = s - a;
+                    Step st;
+                    st.xoff = (unsigned)(j1 * g.xplane + ((u64)a * LC + jc) * g.row);
+                    st.yoff = (unsigned)(m1 * g.yplane + ((u64)(m2 + 1) * LC + mc) * g.row);
+                    st.zrow = (unsigned)(((u64)r1 * D2 + s) * LC + kc);
+                    st.z1ok = s + 1 < D2 ? 1u : 0u;
+                    st.upper = r1 >= T1 ? 1u : 0u;
+                    st.run_start = a == 0;
+                    (kind ? seq_hi : seq_lo)[lane].push_back(st);
+                  }
+                }
+            }
+        }
+      }
+  const size_t len_lo = seq_lo[0].size(), len_hi = seq_hi[0].size();
+  auto steps_of = [&](size_t len) { int n = (int)((len + T - 1) / T); return (n + 1) / 2 * 2; };   // even
+  *n_lo = steps_of(len_lo);
+  *n_hi = steps_of(len_hi);
+  table->assign((size_t)std::max(*n_lo + *n_hi, 2) * NT, make_uint2(0u, 0u));
+  auto emit = [&](const std::vector<Step>& seq, size_t b, size_t e, size_t row0, int tid) {
+    for (size_t i = b; i < e; i++) {
+      const Step& st = seq[i];
+      const bool reload = st.run_start || i == b;
+      uint2 en;
+      en.x = st.xoff | (st.z1ok << 25) | (reload ? SE_RELOAD : 0u) | (st.upper ? SE_UPPER : 0u) | SE_VALID;
+      en.y = st.yoff | (st.zrow << 20);
+      (*table)[(row0 + (i - b)) * NT + tid] = en;
+    }
+  };
+  for (int team = 0; team < T; team++)
+    for (int l = 0; l < nl; l++) {
+      const int tid = team * nl + l;
+      emit(seq_lo[l], len_lo * team / T, len_lo * (team + 1) / T, 0, tid);
+      emit(seq_hi[l], len_hi * team / T, len_hi * (team + 1) / T, (size_t)*n_lo, tid);
+    }
+}
+
 struct SlidePlan {
   BufP table, units;
   unsigned n_units = 0;
@@ -366,16 +480,18 @@ template <int LT> static void slide_launch_lt(Ctx& ctx, const SlidePlan& pl, con
     else GTP_CUDA(cudaFuncSetAttribute(k_mul_slide<LT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.g.smem));
     configured[ch][ctx.device & 63] = pl.g.smem;
   }
-  if (ch) GTP_LAUNCH(ctx, (k_mul_slide<LT, true>), pl.n_units, ST, pl.g.smem, p);
-  else GTP_LAUNCH(ctx, (k_mul_slide<LT, false>), pl.n_units, ST, pl.g.smem, p);
+  if (ch) GTP_LAUNCH(ctx, (k_mul_slide<LT, true>), pl.n_units, pl.g.threads, pl.g.smem, p);
+  else GTP_LAUNCH(ctx, (k_mul_slide<LT, false>), pl.n_units, pl.g.threads, pl.g.smem, p);
 }
 
 void launch_mul_slide(Ctx& ctx, const MulArgs& a) {
   SlideGeom g;
-  GTP_CHECK(slide_geom(a, &g), GTP_ERR_ARG, "sliding product kernel not applicable");
+  GTP_CHECK(slide_geom(ctx, a, &g), GTP_ERR_ARG, "sliding product kernel not applicable");
   SlideKey key;
   key.v.insert(key.v.end(), a.xs.begin(), a.xs.end());
+  key.v.insert(key.v.end(), a.ys.begin(), a.ys.end());
   key.v.insert(key.v.end(), a.rs.begin(), a.rs.end());
+  key.v.push_back(g.T1);
   key.v.push_back(a.row_begin);
   key.v.push_back(a.row_step);
   key.v.push_back(a.row_count);
@@ -390,33 +506,49 @@ void launch_mul_slide(Ctx& ctx, const MulArgs& a) {
     pl->g = g;
     SlideP& p = pl->p;
     memset(&p, 0, sizeof(p));
-    const int nd = g.nd, na = g.na;
-    Shape st(nd, 1);
-    for (int i = nd - 2; i >= 0; --i) st[i] = st[i + 1] * a.xs[i + 1];
-    p.na = na;
-    for (int d = 0; d < na; d++) {
-      p.xa[d] = (unsigned)a.xs[d];
-      p.ya[d] = (unsigned)a.ys[d];
-      p.ra[d] = (unsigned)a.rs[d];
-      p.xastr[d] = p.yastr[d] = (long long)st[d];
+    const int nd = g.nd, nr = g.na, tiled = g.nt > 1 ? 1 : 0, na = nr + tiled;
+    Shape xst(nd, 1), yst(nd, 1);
+    for (int i = nd - 2; i >= 0; --i) {
+      xst[i] = xst[i + 1] * a.xs[i + 1];
+      yst[i] = yst[i + 1] * a.ys[i + 1];
     }
+    // extents of the A axes as the kernel and the unit builder see them (the plane-tile axis last)
+    std::vector<u64> axs(na), ays(na), ars(na);
+    for (int d = 0; d < nr; d++) { axs[d] = a.xs[d]; ays[d] = a.ys[d]; ars[d] = a.rs[d]; }
+    p.na = na;
+    for (int d = 0; d < nr; d++) {
+      p.xastr[d] = (long long)xst[d];
+      p.yastr[d] = (long long)yst[d];
+    }
+    if (tiled) {
+      axs[nr] = ays[nr] = ars[nr] = g.nt;
+      p.xastr[nr] = (long long)(g.T1 * xst[nd - 3]);
+      p.yastr[nr] = (long long)(g.T1 * yst[nd - 3]);
+    }
+    for (int d = 0; d < na; d++) {
+      p.xa[d] = (unsigned)axs[d];
+      p.ya[d] = (unsigned)ays[d];
+      p.ra[d] = (unsigned)ars[d];
+    }
+    p.tiled = tiled;
     p.rows_a0 = (unsigned)a.row_count;
-    p.planes = (unsigned)g.D1;
+    p.planes = (unsigned)g.T1;
     p.prow = (unsigned)(g.D2 * g.lc);
     p.row = (unsigned)g.row;
     p.x_plane_sm = (unsigned)g.xplane; p.y_plane_sm = (unsigned)g.yplane;
     p.x_slab_sm = (unsigned)g.xslab; p.y_slab_sm = (unsigned)g.yslab;
     p.y_first = (unsigned)g.yfirst;
     p.y_up_off = (unsigned)(g.lc * g.row);
-    p.z_rows = (unsigned)(g.D1 * g.D2 * g.lc);
+    p.z_rows = (unsigned)(g.T1 * g.D2 * g.lc);
     p.z_up = (unsigned)g.lc;
     p.G = g.G;
     std::vector<uint2> table;
-    build_slide_table(g, &table, &p.nsteps_lo, &p.nsteps);
+    if (tiled) build_slide_table_tiled(g, &table, &p.nsteps_lo, &p.nsteps);
+    else build_slide_table(g, &table, &p.nsteps_lo, &p.nsteps);
     p.nsteps += p.nsteps_lo;
     // ---- work units (as in kernels_mul_blk.cu) ----
     u64 n_slabs = a.row_count;
-    for (int d = 1; d < na; d++) n_slabs *= a.rs[d];
+    for (int d = 1; d < na; d++) n_slabs *= ars[d];
     auto row_of = [&](u64 idx) -> u64 { return a.rows.empty() ? a.row_begin + idx * a.row_step : a.rows[idx]; };
     struct U { unsigned ka, q0, q1, k0; };
     std::vector<U> units;
@@ -426,12 +558,12 @@ void launch_mul_slide(Ctx& ctx, const MulArgs& a) {
     for (u64 s = 0; s < n_slabs; s++) {
       u64 rem = s, box = 1;
       for (int d = na - 1; d >= 0; --d) {
-        u64 len = (d == 0) ? a.row_count : a.rs[d];
+        u64 len = (d == 0) ? a.row_count : ars[d];
         u64 idx = rem % len;
         rem /= len;
         u64 k = (d == 0) ? row_of(idx) : idx;
         if (d == 0) k0s[s] = (unsigned)k;
-        u64 lo = sat_sub(k + 1, a.ys[d]), hi = std::min(k + 1, a.xs[d]);
+        u64 lo = sat_sub(k + 1, ays[d]), hi = std::min(k + 1, axs[d]);
         box *= hi > lo ? hi - lo : 0;
       }
       boxes[s] = box;

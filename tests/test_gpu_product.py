@@ -94,6 +94,43 @@ def test_blocked_kernel_cubes_match_oracle(ctx, n, d, mode):
     assert rel_err(got, ref) <= RTOL, rel_err(got, ref)
 
 
+TILED_CUBES = [(4, 8, 34), (4, 12, 34), (4, 16, 34), (4, 16, 66), (4, 20, 34), (4, 24, 34), (4, 24, 66), (5, 8, 34), (5, 12, 34)]
+
+
+@pytest.mark.parametrize("n,d,mode", TILED_CUBES)
+def test_tiled_sliding_kernel_cubes_match_oracle(ctx, n, d, mode):
+    """The sliding kernel with a tiled plane axis (mode 2 + 32: 4 planes per staged slab, + 64: 8 planes): interior tile
+    pairs (cyclic plane classes) and the last tile sum (upper output planes masked), 120- and 96-thread CTAs."""
+    from oracle import oracle as O
+    x, y = synth_pgf((d,) * n, 20230517), synth_uniform((d,) * n, 20231210)
+    ctx.set_fast_mul(mode)
+    assert ctx.mul_kernel_kind((d,) * n, (d,) * n, (d,) * n) == 3
+    ref = O.mul_raw(x, y, (d,) * n)
+    got = gpu_mul_raw(ctx, x, y, (d,) * n, fast=mode)
+    assert rel_err(got, ref) <= RTOL, rel_err(got, ref)
+
+
+@pytest.mark.parametrize("mode", [2, 34])
+def test_sliding_kernel_ragged_leading_axes(ctx, mode):
+    """Operands whose leading (A) axes differ: the y strides are the y tensor's own."""
+    from oracle import oracle as O
+    xs, ys, rs = (5, 3, 8, 8, 8), (6, 4, 8, 8, 8), (8, 5, 8, 8, 8)
+    rng = np.random.default_rng(11)
+    x, y = rng.standard_normal(xs), rng.standard_normal(ys)
+    ctx.set_fast_mul(mode)
+    assert ctx.mul_kernel_kind(xs, ys, rs) == 3   # 8 untiled lanes are too few: both modes take the plane-tiled plan
+    ref = O.mul_raw(x, y, rs)
+    got = gpu_mul_raw(ctx, x, y, rs, fast=mode)
+    np.testing.assert_allclose(got, ref, rtol=1e-11, atol=1e-12)
+    xs, ys, rs = (5, 3, 16, 16, 16), (6, 4, 16, 16, 16), (8, 5, 16, 16, 16)
+    x, y = rng.standard_normal(xs), rng.standard_normal(ys)
+    ctx.set_fast_mul(mode)
+    assert ctx.mul_kernel_kind(xs, ys, rs) == 3
+    ref = O.mul_raw(x, y, rs)
+    got = gpu_mul_raw(ctx, x, y, rs, fast=mode)
+    np.testing.assert_allclose(got, ref, rtol=1e-11, atol=1e-12)
+
+
 @pytest.mark.parametrize("n,d", [(4, 12), (4, 16), (5, 12), (5, 16), (4, 8)])
 def test_kernel_selection(ctx, n, d):
     """Dense cube slabs with >= 16 folded lanes take the sliding kernel (3), the rest the blocked one (2)."""
