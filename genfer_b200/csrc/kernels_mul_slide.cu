@@ -64,11 +64,22 @@ template <int LT> __device__ __forceinline__ void sl_load(double (&r)[LT], const
     r[i + 1] = v.y;
   }
 }
+// RED.ADD the accumulator row into HBM and clear it IN PLACE: the "+d" operands pin every accumulator to its register
+// across the (rare, divergent) flush branch, so the merge after it costs no register moves in the hot loop (with plain
+// C++ here ptxas copied all 32 accumulators on every step to set up the merge: ~36 moves + 2 spills per 272 DFMA).
 template <int LT> __device__ __forceinline__ void sl_flush(double (&z)[LT], double* __restrict__ dst, bool write) {
+  const int w = write ? 1 : 0;
 #pragma unroll
-  for (int i = 0; i < LT; i++) {
-    if (write) atomicAdd(dst + i, z[i]);
-    z[i] = 0.0;
+  for (int i = 0; i < LT; i += 2) {
+    asm volatile(
+        "{\n\t.reg .pred pw;\n\tsetp.ne.s32 pw, %3, 0;\n\t"
+        "@pw red.global.add.f64 [%2], %0;\n\t"
+        "@pw red.global.add.f64 [%2+8], %1;\n\t"
+        "mov.f64 %0, 0d0000000000000000;\n\t"
+        "mov.f64 %1, 0d0000000000000000;\n\t}"
+        : "+d"(z[i]), "+d"(z[i + 1])
+        : "l"(dst + i), "r"(w)
+        : "memory");
   }
 }
 // z0 += x (*) ya ; z1 += x (*) yb   (both `lo` or both `hi`)
@@ -169,13 +180,17 @@ __global__ void __launch_bounds__(ST, 3) k_mul_slide(const SlideP p) {
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
 
+    // table entries are fetched one step pair ahead (the table carries two trailing zero rows): their L2 latency
+    // is hidden behind 544 DFMA instead of being exposed at the top of every step pair
+    uint2 n0 = p.table[tid], n1 = p.table[ST + tid];
 #pragma unroll
     for (int ph = 0; ph < (CHUNKED ? 2 : 1); ph++) {
       const bool hi = CHUNKED && ph == 1;
       const int s_begin = hi ? p.nsteps_lo : 0, s_end = hi ? p.nsteps : p.nsteps_lo;
       for (int s = s_begin; s < s_end; s += 2) {
-        const uint2 e0 = p.table[s * ST + tid];
-        const uint2 e1 = p.table[(s + 1) * ST + tid];
+        const uint2 e0 = n0, e1 = n1;
+        n0 = p.table[(s + 2) * ST + tid];
+        n1 = p.table[(s + 3) * ST + tid];
 #pragma unroll
         for (int par = 0; par < 2; par++) {
           const uint2 e = par ? e1 : e0;
@@ -292,13 +307,11 @@ static bool slide_geom(const Ctx& ctx, const MulArgs& a, SlideGeom* g) {
   for (u64 T1 : {4, 8}) {
     if (ctx.slide_tile != 0 && (u64)ctx.slide_tile != T1) continue;
     if (D1 % T1 != 0 || D1 / T1 < 2) continue;
-    const u64 DD = D2 / 4, nl = 8 * DD;
-    if (nl > (u64)ST) continue;
     if (2 * T1 * D2 * g->lc >= 4096) continue;
     g->T1 = T1;
     g->nt = D1 / T1;
     g->E = (int)(8 / T1);
-    g->threads = (int)(nl * ((u64)ST / nl));
+    g->threads = ST;
     g->G = 1;
     slide_smem_layout(g);
     const u64 pair = (g->xslab + g->yslab) * 8;
@@ -367,7 +380,7 @@ static void build_slide_table(const SlideGeom& g, std::vector<uint2>* table, int
   auto steps_of = [&](size_t len) { int n = (int)((len + T - 1) / T); return (n + 1) / 2 * 2; };   // even
   *n_lo = steps_of(len_lo);
   *n_hi = steps_of(len_hi);
-  table->assign((size_t)std::max(*n_lo + *n_hi, 2) * ST, make_uint2(0u, 0u));
+  table->assign((size_t)(std::max(*n_lo + *n_hi, 2) + 2) * ST, make_uint2(0u, 0u));
   auto emit = [&](const std::vector<Step>& seq, size_t b, size_t e, size_t row0, int tid) {
     for (size_t i = b; i < e; i++) {
       const Step& st = seq[i];
@@ -394,7 +407,7 @@ static void build_slide_table(const SlideGeom& g, std::vector<uint2>* table, int
 // conflict-free LDS.128 (plane strides are odd numbers of 16-byte groups).  Lane d of the row-pair fold as untiled.
 static void build_slide_table_tiled(const SlideGeom& g, std::vector<uint2>* table, int* n_lo, int* n_hi) {
   const int T1 = (int)g.T1, E = g.E, D2 = (int)g.D2, P = D2 / 2, DD = P / 2, LC = (int)g.lc;
-  const int nl = 8 * DD, NT = g.threads, T = NT / nl, U = T1 / E;
+  const int nl = 8 * DD, NT = g.threads, U = T1 / E;
   struct Step { unsigned xoff, yoff, zrow, z1ok, upper; bool run_start; };
   std::vector<std::vector<Step>> seq_lo(nl), seq_hi(nl);
   for (int d = 0; d < DD; d++)
@@ -433,14 +446,20 @@ static void build_slide_table_tiled(const SlideGeom& g, std::vector<uint2>* tabl
             }
         }
       }
-  const size_t len_lo = seq_lo[0].size(), len_hi = seq_hi[0].size();
-  auto steps_of = [&](size_t len) { int n = (int)((len + T - 1) / T); return (n + 1) / 2 * 2; };   // even
+  // The sequences of the DD row-fold lanes of one (c, tau) have the same length and structure.  Concatenated over d they
+  // are cut into NT / 8 equal pieces, one per octet of threads: 128-thread CTAs for any D2 (a CTA of 3 warps leaves the
+  // four schedulers of an SM unevenly loaded and its warps wait for each other at the round barrier: 21 % of the
+  // stall samples on 5 x 24), every octet in lockstep on one d at a time.
+  const int NO = NT / 8;
+  const size_t len_lo = seq_lo[0].size() * DD, len_hi = seq_hi[0].size() * DD;
+  auto steps_of = [&](size_t len) { int n = (int)((len + NO - 1) / NO); return (n + 1) / 2 * 2; };   // even
   *n_lo = steps_of(len_lo);
   *n_hi = steps_of(len_hi);
-  table->assign((size_t)std::max(*n_lo + *n_hi, 2) * NT, make_uint2(0u, 0u));
-  auto emit = [&](const std::vector<Step>& seq, size_t b, size_t e, size_t row0, int tid) {
+  table->assign((size_t)(std::max(*n_lo + *n_hi, 2) + 2) * NT, make_uint2(0u, 0u));
+  auto emit = [&](const std::vector<std::vector<Step>>& seqs, int q8, size_t b, size_t e, size_t row0, int tid) {
+    const size_t per = seqs[0].size();
     for (size_t i = b; i < e; i++) {
-      const Step& st = seq[i];
+      const Step& st = seqs[(i / per) * 8 + q8][i % per];
       const bool reload = st.run_start || i == b;
       uint2 en;
       en.x = st.xoff | (st.z1ok << 25) | (reload ? SE_RELOAD : 0u) | (st.upper ? SE_UPPER : 0u) | SE_VALID;
@@ -448,11 +467,11 @@ static void build_slide_table_tiled(const SlideGeom& g, std::vector<uint2>* tabl
       (*table)[(row0 + (i - b)) * NT + tid] = en;
     }
   };
-  for (int team = 0; team < T; team++)
-    for (int l = 0; l < nl; l++) {
-      const int tid = team * nl + l;
-      emit(seq_lo[l], len_lo * team / T, len_lo * (team + 1) / T, 0, tid);
-      emit(seq_hi[l], len_hi * team / T, len_hi * (team + 1) / T, (size_t)*n_lo, tid);
+  for (int o = 0; o < NO; o++)
+    for (int q8 = 0; q8 < 8; q8++) {
+      const int tid = o * 8 + q8;
+      emit(seq_lo, q8, len_lo * o / NO, len_lo * (o + 1) / NO, 0, tid);
+      emit(seq_hi, q8, len_hi * o / NO, len_hi * (o + 1) / NO, (size_t)*n_lo, tid);
     }
 }
 

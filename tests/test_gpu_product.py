@@ -131,13 +131,14 @@ def test_sliding_kernel_ragged_leading_axes(ctx, mode):
     np.testing.assert_allclose(got, ref, rtol=1e-11, atol=1e-12)
 
 
-@pytest.mark.parametrize("n,d", [(4, 12), (4, 16), (5, 12), (5, 16), (4, 8)])
+@pytest.mark.parametrize("n,d", [(4, 12), (4, 16), (5, 12), (5, 16), (4, 8), (4, 24), (4, 10)])
 def test_kernel_selection(ctx, n, d):
-    """Dense cube slabs with >= 16 folded lanes take the sliding kernel (3), the rest the blocked one (2)."""
+    """Dense cube slabs take the sliding kernel (3): whole slabs when they give >= 16 folded lanes and fit in shared
+    memory, plane-tiled otherwise; rows not divisible by 4 go to the blocked kernel (2)."""
     ctx.set_fast_mul(2)
     kind = ctx.mul_kernel_kind((d,) * n, (d,) * n, (d,) * n)
     ctx.set_fast_mul(1)
-    assert kind == (2 if d == 8 else 3)
+    assert kind == (2 if d == 10 else 3)
 
 
 BLK_RAGGED = [((5, 7, 9, 16), (6, 4, 9, 16), (8, 9, 12, 16)), ((3, 5, 16), (4, 2, 16), (6, 6, 16)),
