@@ -282,11 +282,25 @@ __global__ void __launch_bounds__(SD_LANES) k_shift_down_tile(const double* __re
   const unsigned total = lanes * len;
   if ((len & 1u) == 0) {   // rows hold an even number of doubles: the span is 16-byte aligned with the tensor
     const double2* src2 = reinterpret_cast<const double2*>(src);
-    for (unsigned e = threadIdx.x; e < total / 2; e += SD_LANES) {
-      double2 v = src2[e];
-      unsigned o = (2 * e) / len, a = 2 * e - o * len;
-      tile[o * pad + a] = v.x;
-      tile[o * pad + a + 1] = v.y;
+    const unsigned half = total / 2;
+    // batches of 8 independent 16-byte loads per thread before the first shared-memory store: with one load in flight
+    // per thread an SM keeps only ~24 KB in flight, about a third of what HBM3e latency x bandwidth asks for
+    for (unsigned e0 = threadIdx.x; e0 < half; e0 += 8 * SD_LANES) {
+      double2 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const unsigned e = e0 + i * SD_LANES;
+        if (e < half) v[i] = __ldcs(src2 + e);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const unsigned e = e0 + i * SD_LANES;
+        if (e < half) {
+          unsigned o = (2 * e) / len, a = 2 * e - o * len;
+          tile[o * pad + a] = v[i].x;
+          tile[o * pad + a + 1] = v[i].y;
+        }
+      }
     }
   } else {
     for (unsigned e = threadIdx.x; e < total; e += SD_LANES) {

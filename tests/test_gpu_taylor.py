@@ -363,3 +363,41 @@ def test_univariate_matches_oracle(G, n):
     assert ga.coeff(n - 1) == oa.coeff(n - 1)
     assert ga.derivative(min(n - 1, 5)) == oa.derivative(min(n - 1, 5))
     same(ga.taylor_expansion_of_coeff(n // 2), oa.taylor_expansion_of_coeff(n // 2))
+
+
+# ---------------------------------------------------------------------------------------------
+# north_star check 2: the f64 results lie inside the --bounds (Interval<F64>) enclosure
+# ---------------------------------------------------------------------------------------------
+ENCLOSED_OPS = {
+    "mul": lambda x, y: x * y,
+    "div": lambda x, y: x / y,
+    "add_sub": lambda x, y: (x + y) - (y * x),
+    "log_of_product": lambda x, y: (x * y).log(),
+    "exp_of_difference": lambda x, y: (x - y).exp(),
+    "pow5": lambda x, y: x.pow(5),
+    "subst_var": lambda x, y: x.subst_var(1, y),
+    "shift_down": lambda x, y: (x * y).shift_down(0, 2),
+    "derivative": lambda x, y: (x * y).derivative(1, 2),
+    "taylor_expansion_of_coeff": lambda x, y: (x / y).taylor_expansion_of_coeff(0, 1),
+}
+
+
+@pytest.mark.parametrize("name", sorted(ENCLOSED_OPS))
+@pytest.mark.parametrize("shape", [(5, 5), (3, 4, 3), (12, 12)])
+def test_gpu_results_inside_interval_enclosure(G, name, shape):
+    """The device f64 result of every operator family must fall inside the result of the same operator over
+    Interval<F64> (src/interval.rs, restated in the oracle) started from point intervals: the property the reference's
+    --bounds mode guarantees for its own f64 path.  Covers the DFMA product kernels too (mode 2 forces them): fused
+    multiply-add rounds once, the enclosure is of the exact result, so it must still contain it."""
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(repr((name, shape)).encode()))
+    a, b = rng.uniform(0.5, 2.0, shape), rng.uniform(0.5, 2.0, shape)
+    op = ENCLOSED_OPS[name]
+    iv = op(O().TaylorPoly.new(np.stack([a, a], -1), shape, kind="iv"),
+            O().TaylorPoly.new(np.stack([b, b], -1), shape, kind="iv")).array()
+    for mode in (0, 1, 2):
+        G.default_context().set_fast_mul(mode)
+        got = op(G.TaylorPoly.new(a, shape), G.TaylorPoly.new(b, shape)).array()
+        G.default_context().set_fast_mul(1)
+        assert got.shape == iv.shape[:-1]
+        assert np.all(iv[..., 0] <= got) and np.all(got <= iv[..., 1]), (name, mode)
