@@ -258,8 +258,22 @@ PolyP mul_var(Ctx& c, const gtp_poly& self, const double* m_dev, u64 v, const Sh
   launch_ew(c, EW_SCALE_DEV, ext, A, nullptr, r->buf->d, shape, olo, -1, nullptr, nullptr, m_dev);
   return r;
 }
-PolyP mul_linear(Ctx& c, const gtp_poly& self, double cst, const double* m_dev, u64 v, const Shape& shape,
+PolyP mul_linear(Ctx& c, const gtp_poly& self, double cst, double m, const double* m_dev, u64 v, const Shape& shape,
                  const Shape& degrees) {
+  // One fused pass when the result keeps the shape of `self` on every other axis and neither side of the reference's
+  // `mul_var(..) + self * c` would take a scalar fast path (those have their own rounding / signed-zero behaviour).
+  bool fused = self.len() > 1 && prod(shape) > 1 && prod(shape) < (1ull << 32) - 4096 && shape.size() == self.shape.size() &&
+               (shape[v] == self.shape[v] || shape[v] == self.shape[v] + 1) && c.fuse_mul_linear;
+  for (size_t a = 0; fused && a < shape.size(); a++)
+    if (a != v && shape[a] != self.shape[a]) fused = false;
+  if (fused) {
+    PolyP r = new_uninit(c, shape, degrees);
+    u64 outer = 1, inner = 1;
+    for (size_t a = 0; a < v; a++) outer *= shape[a];
+    for (size_t a = v + 1; a < shape.size(); a++) inner *= shape[a];
+    launch_mul_linear(c, self.ptr(), r->buf->d, outer, self.shape[v], shape[v], inner, cst, m);
+    return r;
+  }
   if (cst == 0.0) return mul_var(c, self, m_dev, v, shape, degrees);
   PolyP shifted = mul_var(c, self, m_dev, v, shape, degrees);
   PolyP cpoly = scalar_poly(c, cst, {}, {});
@@ -284,14 +298,14 @@ PolyP poly_mul(Ctx& c, const gtp_poly& a0, const gtp_poly& b0) {
     u64 v = at->cls->v;
     Shape s = bt->shape;
     s[v] = std::min(d[v], s[v] + 1);
-    return mul_linear(c, *bt, at->cls->c, at->ptr() + stride_of(at->shape, v), v, s, d);
+    return mul_linear(c, *bt, at->cls->c, at->cls->m, at->ptr() + stride_of(at->shape, v), v, s, d);
   }
   classify(c, *bt);
   if (bt->cls->linear) {  // :1057-1061
     u64 v = bt->cls->v;
     Shape s = at->shape;
     s[v] = std::min(d[v], s[v] + 1);
-    return mul_linear(c, *at, bt->cls->c, bt->ptr() + stride_of(bt->shape, v), v, s, d);
+    return mul_linear(c, *at, bt->cls->c, bt->cls->m, bt->ptr() + stride_of(bt->shape, v), v, s, d);
   }
   // general case (:1064-1070)
   PolyP r = new_uninit(c, shape, d);
@@ -513,13 +527,18 @@ PolyP slice_scale(Ctx& c, const gtp_poly& a, u64 v, u64 n, int kind) {
   Shape ext = a.shape, lo(a.shape.size(), 0);
   ext[v] = a.shape[v] - n;
   lo[v] = n;
-  BufP fac = c.alloc(ext[v]);
-  launch_factors(c, kind, n, ext[v], nullptr, fac->d);
   PolyP r = new_uninit(c, ext, d);
   EwOperand A;
   A.p = a.ptr();
   A.shape = a.shape;
   A.lo = lo;
+  double tab[256];
+  if (prod(ext) < (1ull << 32) - 4096 && host_factors(kind, n, ext[v], tab)) {   // one launch: the table rides in the parameters
+    launch_ew(c, EW_COPY, ext, A, nullptr, r->buf->d, ext, {}, (int)v, nullptr, nullptr, nullptr, tab, (int)ext[v]);
+    return r;
+  }
+  BufP fac = c.alloc(ext[v]);
+  launch_factors(c, kind, n, ext[v], nullptr, fac->d);
   launch_ew(c, EW_COPY, ext, A, nullptr, r->buf->d, ext, {}, (int)v, fac->d);
   return r;
 }
@@ -685,6 +704,7 @@ int gtp_ctx_set_fast_mul(gtp_ctx* c, int enabled) {
   c->blk_fold_tables = (enabled & 4) == 0;
   c->blk_octet = (enabled & 8) != 0;   // experimental
   c->use_slide = (enabled & 16) == 0;
+  c->fuse_mul_linear = (enabled & 128) == 0;
   c->slide_tile = ((enabled >> 5) & 3) == 1 ? 4 : (((enabled >> 5) & 3) == 2 ? 8 : 0);   // A/B measurements
   enabled &= 3;
   c->fast_mul = enabled < 0 ? 0 : (enabled > 2 ? 2 : enabled);

@@ -56,9 +56,14 @@ struct EwOperand {
 };
 void launch_ew(Ctx& ctx, EwOp op, const Shape& box, const EwOperand& a, const EwOperand* b,
                double* out, const Shape& out_shape, const Shape& out_lo, int fax = -1,
-               const double* fac = nullptr, const unsigned char* keep = nullptr, const double* s = nullptr);
+               const double* fac = nullptr, const unsigned char* keep = nullptr, const double* s = nullptr,
+               const double* host_tab = nullptr, int host_tab_len = 0);   // host_tab: factor table by kernel parameter
+// derivative / binomial factor tables of at most 256 entries built on the host (kinds 0 and 1 of launch_factors)
+bool host_factors(int kind, u64 n, u64 len, double* fac);
 
 void launch_fill(Ctx& ctx, double* dst, u64 n, double value);
+// fused mul_linear / mul_var (:589-623) on the (outer, xlen, inner) view of the variable's axis; out has olen (xlen or xlen + 1) slices
+void launch_mul_linear(Ctx& ctx, const double* x, double* out, u64 outer, u64 xlen, u64 olen, u64 inner, double c, double m);
 // fac[k], k < len:  kind 0: falling factorials (n+k)!/k!  (derivative :472-479)
 //                   kind 1: binomials C(n+k,k)            (taylor_expansion_of_coeff :499-507)
 //                   kind 2: powers (*m)^k                 (subst_var linear path :557-565)

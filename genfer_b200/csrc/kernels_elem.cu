@@ -58,6 +58,118 @@ __global__ void __launch_bounds__(256) k_ew(const EwParams p) {
   }
 }
 
+// Fast variant (every tensor with fewer than 2^32 box elements): 32-bit index arithmetic, four independent elements per
+// thread and iteration (all loads issued before the first store: the one-element loop above keeps a single 8-byte load
+// in flight per thread and reaches ~64 % of HBM on a plain copy), and -- when the innermost axis is contiguous, even
+// and 16-byte aligned in every tensor (VEC2) -- 16-byte loads and stores.  `tab` is a factor table passed in the
+// kernel parameters (host-built derivative / binomial factors: no table-building launch); fac == nullptr, tab == nullptr:
+// no factor.  Arithmetic is identical to k_ew.
+struct FacTab {
+  double f[256];
+};
+template <int OP, bool VEC2>
+__device__ __forceinline__ void ew_fast_body(const EwParams& p, const double* __restrict__ fac) {
+  constexpr int U = 4;
+  const unsigned units = (unsigned)p.total;   // elements, or element pairs along the innermost axis (VEC2)
+  const unsigned step = blockDim.x * U;
+  for (unsigned base = blockIdx.x * step + threadIdx.x; base < units; base += gridDim.x * step) {
+    long long ao[U], bo[U], oo[U];
+    bool a_ok[U], b_ok[U], live[U];
+    unsigned fidx[U];
+#pragma unroll
+    for (int j = 0; j < U; j++) {
+      const unsigned lin = base + j * blockDim.x;
+      live[j] = lin < units;
+      unsigned rem = live[j] ? lin : 0u;
+      ao[j] = p.a_base;
+      bo[j] = p.b_base;
+      oo[j] = p.o_base;
+      a_ok[j] = b_ok[j] = true;
+      fidx[j] = 0;
+#pragma unroll 1
+      for (int d = p.ndim - 1; d >= 0; --d) {
+        const unsigned e = p.ext[d];
+        const unsigned q = rem / e, i = rem - q * e;
+        rem = q;
+        const unsigned ii = (VEC2 && d == p.ndim - 1) ? 2u * i : i;
+        ao[j] += (long long)ii * p.a_str[d];
+        bo[j] += (long long)ii * p.b_str[d];
+        oo[j] += (long long)ii * p.o_str[d];
+        a_ok[j] &= ii < p.a_ext[d];
+        b_ok[j] &= ii < p.b_ext[d];
+        if (d == p.fax) fidx[j] = ii;
+      }
+    }
+    double2 av[U], bv[U];
+    constexpr bool READS_A_ALWAYS = !(OP == EW_ADD || OP == EW_SUB);
+    constexpr bool READS_B = (OP == EW_ADD || OP == EW_SUB);
+#pragma unroll
+    for (int j = 0; j < U; j++) {
+      av[j] = bv[j] = make_double2(0.0, 0.0);
+      if (live[j] && (READS_A_ALWAYS || a_ok[j])) {
+        if (VEC2) av[j] = *reinterpret_cast<const double2*>(p.a + ao[j]);
+        else av[j].x = p.a[ao[j]];
+      }
+      if (READS_B && live[j] && b_ok[j]) {
+        if (VEC2) bv[j] = *reinterpret_cast<const double2*>(p.b + bo[j]);
+        else bv[j].x = p.b[bo[j]];
+      }
+    }
+    double sv = 0.0;
+    if (OP == EW_SCALE_DEV || OP == EW_DIV_DEV || OP == EW_ADD_FIRST || OP == EW_SUB_FIRST || OP == EW_RSUB_FIRST) sv = *p.s;
+#pragma unroll
+    for (int j = 0; j < U; j++) {
+      if (!live[j]) continue;
+      const bool first = (base + j * blockDim.x) == 0;
+      double2 r;
+#pragma unroll
+      for (int h = 0; h < (VEC2 ? 2 : 1); h++) {
+        const double a = h ? av[j].y : av[j].x, b = h ? bv[j].y : bv[j].x;
+        const bool f0 = first && h == 0;
+        double v;
+        if (OP == EW_COPY) {
+          const bool last_fax = p.fax == p.ndim - 1;
+          v = fac ? __dmul_rn(a, fac[fidx[j] + ((VEC2 && last_fax) ? h : 0)]) : a;
+        } else if (OP == EW_ADD || OP == EW_SUB) {
+          v = 0.0;
+          if (a_ok[j]) v = __dadd_rn(v, a);
+          if (b_ok[j]) v = (OP == EW_ADD) ? __dadd_rn(v, b) : __dsub_rn(v, b);
+        } else if (OP == EW_MASK) {
+          const bool last_fax = p.fax == p.ndim - 1;
+          v = p.keep[fidx[j] + ((VEC2 && last_fax) ? h : 0)] ? a : 0.0;
+        } else if (OP == EW_SCALE_DEV) {
+          v = __dmul_rn(sv, a);
+        } else if (OP == EW_DIV_DEV) {
+          v = __ddiv_rn(a, sv);
+        } else if (OP == EW_NEG) {
+          v = -a;
+        } else if (OP == EW_ADD_FIRST) {
+          v = f0 ? __dadd_rn(a, sv) : a;
+        } else if (OP == EW_SUB_FIRST) {
+          v = f0 ? __dsub_rn(a, sv) : a;
+        } else {  // EW_RSUB_FIRST
+          v = -(f0 ? __dsub_rn(a, sv) : a);
+        }
+        if (h) r.y = v; else r.x = v;
+      }
+      if (VEC2) *reinterpret_cast<double2*>(p.out + oo[j]) = r;
+      else p.out[oo[j]] = r.x;
+    }
+  }
+}
+template <int OP, bool VEC2>
+__global__ void __launch_bounds__(256) k_ew_fast(const __grid_constant__ EwParams p) {
+  ew_fast_body<OP, VEC2>(p, p.fac);
+}
+template <bool VEC2>
+__global__ void __launch_bounds__(256) k_ew_tab(const __grid_constant__ EwParams p, const __grid_constant__ FacTab tab) {
+  // staged in shared memory: a warp's lanes index the table with different k, and divergent constant-bank reads serialise
+  __shared__ double sfac[256];
+  sfac[threadIdx.x] = tab.f[threadIdx.x];
+  __syncthreads();
+  ew_fast_body<EW_COPY, VEC2>(p, sfac);
+}
+
 static Shape strides_of(const Shape& shape) {
   Shape st(shape.size(), 1);
   for (int i = (int)shape.size() - 2; i >= 0; --i) st[i] = st[i + 1] * shape[i + 1];
@@ -66,7 +178,7 @@ static Shape strides_of(const Shape& shape) {
 
 void launch_ew(Ctx& ctx, EwOp op, const Shape& box, const EwOperand& a, const EwOperand* b, double* out,
                const Shape& out_shape, const Shape& out_lo, int fax, const double* fac,
-               const unsigned char* keep, const double* s) {
+               const unsigned char* keep, const double* s, const double* tab, int tab_len) {
   const int nd = (int)box.size();
   GTP_CHECK(nd <= MAXD, GTP_ERR_ARG, "ndim exceeds GTP_MAX_NDIM");
   u64 total = prod(box);
@@ -139,6 +251,40 @@ void launch_ew(Ctx& ctx, EwOp op, const Shape& box, const EwOperand& a, const Ew
   p.keep = keep;
   p.s = s;
   int block = 256;
+  if (total < (1ull << 32) - 4096) {
+    // innermost axis contiguous, even and 16-byte aligned everywhere: element pairs
+    const int l = p.ndim - 1;
+    auto even_off = [&](long long base, const long long* str, const double* ptr) {
+      if (!ptr) return true;
+      if ((reinterpret_cast<uintptr_t>(ptr) & 15u) || (base & 1)) return false;
+      for (int d = 0; d < l; d++)
+        if (str[d] & 1) return false;
+      return str[l] == 1;
+    };
+    bool vec2 = (p.ext[l] % 2 == 0) && (p.a_ext[l] % 2 == 0) && (!b || p.b_ext[l] % 2 == 0) &&
+                even_off(p.a_base, p.a_str, p.a) && even_off(p.o_base, p.o_str, p.out) && (!b || even_off(p.b_base, p.b_str, p.b));
+    if (vec2) {
+      p.ext[l] /= 2;
+      p.total = total / 2;
+    }
+    const u64 units = p.total;
+    int grid = (int)std::max<u64>(1, std::min<u64>((units + block * 4 - 1) / (block * 4), (u64)ctx.sm_count * 16));
+    if (op == EW_COPY && tab) {
+      FacTab t;
+      memcpy(t.f, tab, sizeof(double) * tab_len);
+      if (vec2) GTP_LAUNCH(ctx, k_ew_tab<true>, grid, block, 0, p, t);
+      else GTP_LAUNCH(ctx, k_ew_tab<false>, grid, block, 0, p, t);
+      return;
+    }
+    switch (op) {
+#define CASE(O) case O: if (vec2) GTP_LAUNCH(ctx, (k_ew_fast<O, true>), grid, block, 0, p); else GTP_LAUNCH(ctx, (k_ew_fast<O, false>), grid, block, 0, p); break;
+      CASE(EW_COPY) CASE(EW_ADD) CASE(EW_SUB) CASE(EW_MASK) CASE(EW_SCALE_DEV) CASE(EW_DIV_DEV)
+      CASE(EW_NEG) CASE(EW_ADD_FIRST) CASE(EW_SUB_FIRST) CASE(EW_RSUB_FIRST)
+#undef CASE
+    }
+    return;
+  }
+  GTP_CHECK(!tab, GTP_ERR_ARG, "host factor tables need the fast element-wise path");
   u64 want = (total + block - 1) / block;
   int grid = (int)std::min<u64>(want, (u64)ctx.sm_count * 16);
   switch (op) {
@@ -147,6 +293,82 @@ void launch_ew(Ctx& ctx, EwOp op, const Shape& box, const EwOperand& a, const Ew
     CASE(EW_NEG) CASE(EW_ADD_FIRST) CASE(EW_SUB_FIRST) CASE(EW_RSUB_FIRST)
 #undef CASE
   }
+}
+
+// Host-built factor tables (plain IEEE double multiplications and divisions in the reference's incremental order, so
+// bit-identical to k_factors): up to 256 entries travel in the kernel parameters.
+bool host_factors(int kind, u64 n, u64 len, double* fac) {
+  if (len > 256 || kind > 1) return false;
+  if (kind == 0) {  // derivative :472-479
+    volatile double ff = 1.0;
+    for (u64 i = 1; i <= n; i++) ff = ff * (double)(unsigned)i;
+    for (u64 k = 0; k < len; k++) {
+      fac[k] = ff;
+      volatile double q = (double)(unsigned)(n + k + 1) / (double)(unsigned)(k + 1);
+      ff = ff * q;
+    }
+  } else {  // taylor_expansion_of_coeff :499-507
+    volatile double f = 1.0;
+    fac[0] = 1.0;
+    for (u64 k = 1; k < len; k++) {
+      volatile double q = (double)(unsigned)(n + k) / (double)(unsigned)k;
+      f = f * q;
+      fac[k] = f;
+    }
+  }
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// mul_linear (:611-623) in one pass over the (outer, len, inner) view of axis v:
+//   out[o,k,i] = (0 + m x[o,k-1,i]) + c x[o,k,i]      k < xlen     (Add of `mul_var` and `self * c`, :873-880)
+//              =  0 + m x[o,k-1,i]                    k == xlen    (the result is one slice longer than x)
+//   c == 0:   out[o,k,i] = m x[o,k-1,i]  (mul_var alone, :589-608; slice 0 is +0)
+// Same products, same additions and the same zero-extension as the reference's composition (which costs a memset and
+// four more passes over HBM); x[.,k-1,.] is re-read from L1/L2.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_mul_linear(const double* __restrict__ x, double* __restrict__ out, unsigned total,
+                                                   unsigned xlen, unsigned olen, unsigned inner, double c, double m, int var_only) {
+  constexpr int U = 4;
+  const unsigned step = blockDim.x * U;
+  for (unsigned base = blockIdx.x * step + threadIdx.x; base < total; base += gridDim.x * step) {
+    double cur[U], prev[U];
+    unsigned kk[U];
+#pragma unroll
+    for (int j = 0; j < U; j++) {
+      const unsigned lin = base + j * blockDim.x;
+      cur[j] = prev[j] = 0.0;
+      kk[j] = 0;
+      if (lin < total) {
+        const unsigned q = lin / inner, i = lin - q * inner;
+        const unsigned o = q / olen, k = q - o * olen;
+        kk[j] = k;
+        const size_t at = ((size_t)o * xlen + k) * inner + i;
+        if (k < xlen && !var_only) cur[j] = x[at];
+        if (k >= 1) prev[j] = x[at - inner];     // k <= xlen always (olen <= xlen + 1)
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < U; j++) {
+      const unsigned lin = base + j * blockDim.x;
+      if (lin >= total) continue;
+      const double sh = kk[j] >= 1 ? __dmul_rn(prev[j], m) : 0.0;
+      double r;
+      if (var_only) r = sh;
+      else {
+        r = __dadd_rn(0.0, sh);
+        if (kk[j] < xlen) r = __dadd_rn(r, __dmul_rn(c, cur[j]));
+      }
+      out[lin] = r;
+    }
+  }
+}
+void launch_mul_linear(Ctx& ctx, const double* x, double* out, u64 outer, u64 xlen, u64 olen, u64 inner, double c, double m) {
+  const u64 total = outer * olen * inner;
+  if (total == 0) return;
+  int grid = (int)std::max<u64>(1, std::min<u64>((total + 1023) / 1024, (u64)ctx.sm_count * 16));
+  GTP_LAUNCH(ctx, k_mul_linear, grid, 256, 0, x, out, (unsigned)total, (unsigned)xlen, (unsigned)olen, (unsigned)inner, c, m,
+             c == 0.0 ? 1 : 0);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -275,10 +275,14 @@ class TaylorPoly:
     def _coerce(self, o) -> "TaylorPoly":
         return o if isinstance(o, TaylorPoly) else TaylorPoly.from_scalar(float(o), self.ctx)
 
-    def __add__(self, o): return self._op("gtp_add", self._coerce(o)._h)
-    def __sub__(self, o): return self._op("gtp_sub", self._coerce(o)._h)
-    def __mul__(self, o): return self._op("gtp_mul", self._coerce(o)._h)
-    def __truediv__(self, o): return self._op("gtp_div", self._coerce(o)._h)
+    def _binop(self, fn: str, o) -> "TaylorPoly":
+        other = self._coerce(o)          # keep a coerced scalar alive across the call (its __del__ frees the handle)
+        return self._op(fn, other._h)
+
+    def __add__(self, o): return self._binop("gtp_add", o)
+    def __sub__(self, o): return self._binop("gtp_sub", o)
+    def __mul__(self, o): return self._binop("gtp_mul", o)
+    def __truediv__(self, o): return self._binop("gtp_div", o)
     def __neg__(self): return self._op("gtp_neg")
 
     def __eq__(self, other) -> bool:  # derive(PartialEq) (:10)

@@ -401,3 +401,45 @@ def test_gpu_results_inside_interval_enclosure(G, name, shape):
         G.default_context().set_fast_mul(1)
         assert got.shape == iv.shape[:-1]
         assert np.all(iv[..., 0] <= got) and np.all(got <= iv[..., 1]), (name, mode)
+
+
+@pytest.mark.parametrize("shape,deg", [((6,), (6,)), ((6,), (9,)), ((4, 5), (4, 5)), ((4, 5), (6, 7)), ((3, 4, 5), (3, 5, 5)),
+                                       ((2, 3, 4, 5), (4, 4, 4, 6)), ((33, 17), (40, 17)), ((1, 7), (3, 8))])
+def test_mul_linear_fused_bit_exact(G, shape, deg):
+    """Mul by `c + m eps_v` (:1052-1061 -> mul_linear :611-623): the one-pass kernel, the reference's composition
+    (mode bit 128 switches the fused kernel off) and the oracle agree bit for bit, for every variable, for c == 0
+    (mul_var alone), with the result capped by degrees_p1 or one slice longer, and with signed zeros in the data."""
+    rng = np.random.default_rng(len(shape) * 1000 + sum(shape))
+    a = rng.standard_normal(shape)
+    a.flat[rng.integers(0, a.size, max(1, a.size // 7))] = -0.0
+    a.flat[rng.integers(0, a.size, max(1, a.size // 9))] = 0.0
+    ctx = G.default_context()
+    for v in range(len(shape)):
+        for c0, m in ((0.5, -1.5), (0.0, 2.0), (1.0, 1.0), (-2.0, 0.25)):
+            lin_shape = [1] * len(shape)
+            lin_shape[v] = 2
+            lin = np.zeros(lin_shape)
+            lin.flat[0], lin.flat[1] = c0, m
+            results = []
+            for mode in (1, 129):
+                ctx.set_fast_mul(mode)
+                x, ox = both(G, a, deg)
+                l, ol = both(G, lin, deg)
+                results.append(((x * l), (l * x)))
+            ctx.set_fast_mul(1)
+            ref = ox * ol
+            for r1, r2 in results:
+                assert_same(r1, ref)
+                assert_same(r2, ol * ox)
+
+
+def test_python_scalar_operands_stay_alive(G):
+    """`poly * 0.75` coerces the float to a temporary TaylorPoly; it must outlive the C call (it used to be freed
+    between argument evaluation and the call)."""
+    a = np.arange(12.0).reshape(3, 4) + 1.0
+    g, o = both(G, a)
+    for _ in range(50):
+        assert_same(g * 0.75, o * O().TaylorPoly.from_scalar(0.75))
+        assert_same(g + 2.0, o + O().TaylorPoly.from_scalar(2.0))
+        assert_same(g - 0.5, o - O().TaylorPoly.from_scalar(0.5))
+        assert_same(g / 4.0, o / O().TaylorPoly.from_scalar(4.0))
