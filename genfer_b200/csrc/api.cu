@@ -208,7 +208,8 @@ PolyP ew_scalar(Ctx& c, EwOp op, const gtp_poly& a, const double* s, const Shape
 
 PolyP poly_add(Ctx& c, const gtp_poly& a0, const gtp_poly& b0, bool subtract);
 PolyP poly_mul(Ctx& c, const gtp_poly& a0, const gtp_poly& b0);
-PolyP poly_div(Ctx& c, const gtp_poly& a0, const gtp_poly& b0);
+PolyP poly_div(Ctx& c, const gtp_poly& a0, const gtp_poly& b0, PolyP* recip_cache = nullptr);
+PolyP poly_recip(Ctx& c, const gtp_poly& y, const Shape& ws);
 
 // ---- Add / Sub (:854-937) --------------------------------------------------------------------------
 PolyP poly_add(Ctx& c, const gtp_poly& a0, const gtp_poly& b0, bool subtract) {
@@ -325,7 +326,7 @@ PolyP poly_mul(Ctx& c, const gtp_poly& a0, const gtp_poly& b0) {
 }
 
 // ---- Div (:1194-1231) ----------------------------------------------------------------------------------
-PolyP poly_div(Ctx& c, const gtp_poly& a0, const gtp_poly& b0) {
+PolyP poly_div(Ctx& c, const gtp_poly& a0, const gtp_poly& b0, PolyP* recip_cache) {
   gtp_poly a = a0, b = b0;
   broadcast(a, b);
   Shape d = min_degrees(a, b);  // after broadcast (:1199-1200)
@@ -346,8 +347,29 @@ PolyP poly_div(Ctx& c, const gtp_poly& a0, const gtp_poly& b0) {
     for (size_t i = axis + 1; i < rs.size(); i++) inner *= rs[i];
     launch_div_axis(c, at->ptr(), bt->ptr(), r->buf->d, outer, inner, at->shape[axis], bt->shape[axis], rs[axis],
                     at->shape, rs, axis);
+  } else if (c.fast_mul == 0) {
+    launch_div_general(c, at->ptr(), at->shape, bt->ptr(), bt->shape, r->buf->d, rs);   // exact-order mode: wavefront kernel
   } else {
-    launch_div_general(c, at->ptr(), at->shape, bt->ptr(), bt->shape, r->buf->d, rs);
+    // x / y = x (*) (1 / y): the reciprocal series costs 2 products per slice of every non-unit axis (recip_rec), all of
+    // them on the product kernels; the wavefront kernel keeps a few thousand threads busy and is slower than one host
+    // core beyond ~10^4 coefficients.  Same value in exact arithmetic, tolerance-checked like the DFMA products.
+    Shape ws = rs;
+    for (size_t i = 0; i < ws.size(); i++)
+      if (bt->shape[i] == 1) ws[i] = 1;
+    PolyP w = (recip_cache && *recip_cache) ? share(**recip_cache) : poly_recip(c, *bt, ws);
+    if (recip_cache && !*recip_cache) *recip_cache = share(*w);
+    MulArgs m;
+    m.ndim = (int)rs.size();
+    m.xs = at->shape;
+    m.ys = ws;
+    m.rs = rs;
+    m.x = at->ptr();
+    m.y = w->ptr();
+    m.out = r->buf->d;
+    m.row_begin = 0;
+    m.row_step = 1;
+    m.row_count = rs.empty() ? 1 : rs[0];
+    launch_mul(c, m);
   }
   return r;
 }
@@ -370,6 +392,71 @@ u64 tail_prod(const Shape& s, size_t from) {
   return p;
 }
 Shape tail(const Shape& s, size_t from) { return Shape(s.begin() + from, s.end()); }
+
+// ---- reciprocal series (for the general Div) ---------------------------------------------------------------
+// W = 1 / Y on the sub-views ys[from..] / ws[from..]:  W[0] = 1 / Y[0] (one axis less);
+// W[k] = -(sum_{j<k} W[j] (*) Y[k-j]) (*) W[0]   -- the reference's div recurrence (:1170-1191) for X = 1 with the inner
+// division by Y[0] replaced by a product with its reciprocal.  ws[i] == 1 wherever Y is constant along axis i.
+void recip_rec(Ctx& c, const double* yp, const Shape& ys, double* wp, const Shape& ws, size_t from, const double* one_dev) {
+  const size_t nd = ws.size();
+  int nonunit = 0, axis = -1;
+  for (size_t i = from; i < nd; i++)
+    if (ws[i] != 1) { nonunit++; axis = (int)i; }
+  if (nonunit <= 1) {   // scalar or one varying axis: the single-axis division kernel with X = 1 (bit-exact recurrence)
+    const u64 rl = nonunit ? ws[axis] : 1, yl = nonunit ? ys[axis] : 1;
+    Shape one_shape(nd - from, 1), w_shape = tail(ws, from);
+    launch_div_axis(c, one_dev, yp, wp, 1, 1, 1, yl, rl, one_shape, w_shape, nonunit ? axis - (int)from : 0);
+    return;
+  }
+  const u64 ystr = tail_prod(ys, from + 1), wstr = tail_prod(ws, from + 1);
+  recip_rec(c, yp, ys, wp, ws, from + 1, one_dev);
+  const u64 yl = ys[from], wl = ws[from];
+  if (wl <= 1) return;
+  BufP tmp = c.alloc(std::max<u64>(wstr, 1));
+  Shape sub = tail(ws, from + 1);
+  for (u64 k = 1; k < wl; k++) {
+    double* cur = wp + k * wstr;
+    if (yl <= 1) {
+      GTP_CUDA(cudaMemsetAsync(cur, 0, wstr * sizeof(double), c.stream));
+      continue;
+    }
+    // S = sum_{j<k} W[j] (*) Y[k-j] = leading-axis row k-1 of Y[1..] (*) W[0..k)
+    MulArgs m;
+    m.ndim = (int)(nd - from);
+    m.xs = tail(ys, from);
+    m.xs[0] = yl - 1;
+    m.ys = tail(ws, from);
+    m.ys[0] = k;
+    m.rs = tail(ws, from);
+    m.x = yp + ystr;
+    m.y = wp;
+    m.out = tmp->d;
+    m.row_begin = k - 1;
+    m.row_step = 1;
+    m.row_count = 1;
+    launch_mul(c, m);
+    // W[k] = -(S (*) W[0])
+    MulArgs q;
+    q.ndim = (int)sub.size();
+    q.xs = sub;
+    q.ys = sub;
+    q.rs = sub;
+    q.x = tmp->d;
+    q.y = wp;
+    q.out = cur;
+    q.row_begin = 0;
+    q.row_step = 1;
+    q.row_count = sub.empty() ? 1 : sub[0];
+    launch_mul(c, q);
+    launch_scale_const(c, cur, cur, wstr, -1.0, false);
+  }
+}
+PolyP poly_recip(Ctx& c, const gtp_poly& y, const Shape& ws) {
+  PolyP one = scalar_poly(c, 1.0, {}, {});
+  PolyP w = new_uninit(c, ws, ws);
+  recip_rec(c, y.ptr(), y.shape, w->buf->d, ws, 0, one->ptr());
+  return w;
+}
 
 // exp (:1285-1317) on the sub-views xs[from..] / res[from..] located at xp / rp
 void exp_rec(Ctx& c, const double* xp, const Shape& xs, double* rp, const Shape& rs, size_t from) {
@@ -450,6 +537,7 @@ void log_rec(Ctx& c, const double* xp, const Shape& xs, double* rp, const Shape&
     b->owned = false;
     den->buf = b;
   }
+  PolyP den_recip;
   for (u64 k = 1; k < rl; k++) {
     double* cur = rp + k * rstr;
     u64 lo = std::max<u64>(sat_sub(k + 1, xl), 1);
@@ -499,7 +587,7 @@ void log_rec(Ctx& c, const double* xp, const Shape& xs, double* rp, const Shape&
       launch_ew(c, EW_ADD, cur_shape, A, &B, sum->buf->d, cur_shape, {});
       numer = std::move(sum);
     }
-    PolyP q = poly_div(c, *numer, *den);  // full Div dispatch (:1376-1383)
+    PolyP q = poly_div(c, *numer, *den, &den_recip);  // full Div dispatch (:1376-1383); 1 / xs[0] is computed once
     GTP_CHECK(q->shape == cur_shape, GTP_ERR_SHAPE, "log: quotient shape mismatch");
     launch_scale_const(c, q->ptr(), cur, rstr, (double)k, true);                 // current /= k (:1384)
     launch_scale_const(c, cur, rscaled->d + k * rstr, rstr, (double)k, false);    // RS[k] = res[k] * k

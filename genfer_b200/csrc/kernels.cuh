@@ -105,6 +105,10 @@ struct MulArgs {
 void launch_mul(Ctx& ctx, const MulArgs& a);
 int mul_kernel_kind(const Ctx& ctx, const MulArgs& a);
 double mul_macs(const Shape& xs, const Shape& ys, const Shape& rs);
+double args_macs(const MulArgs& a);   // MACs of the rows this launch computes
+// Products below this many MACs stay on the reference-order kernel (bit-exact, and launch-bound anyway); above it the
+// DFMA kernels run even when only a few slabs exist (their units split the j box, so a handful of slabs still fills the SMs)
+constexpr double DFMA_MIN_MACS = 1 << 20;
 void fp64_peak_probe(Ctx& ctx, int kind, int iters, double* flops, double* ms);
 
 // ---------------------------------------------------------------------------------------------

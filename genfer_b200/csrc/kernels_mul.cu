@@ -94,6 +94,26 @@ __global__ void __launch_bounds__(128) k_mul_ordered(const MulP p) {
   }
 }
 
+// MACs of the rows a launch computes (the `lo..hi` trip counts of :975-977, :1002-1004)
+double args_macs(const MulArgs& a) {
+  double total = 1.0;
+  for (int d = 0; d < a.ndim; d++) {
+    double s = 0;
+    auto trips = [&](u64 k) {
+      u64 lo = sat_sub(k + 1, a.ys[d]), hi = std::min<u64>(k + 1, a.xs[d]);
+      return hi > lo ? (double)(hi - lo) : 0.0;
+    };
+    if (d == 0) {
+      if (!a.rows.empty()) for (u64 k : a.rows) s += trips(k);
+      else for (u64 i = 0; i < a.row_count; i++) s += trips(a.row_begin + i * a.row_step);
+    } else {
+      for (u64 k = 0; k < a.rs[d]; k++) s += trips(k);
+    }
+    total *= s;
+  }
+  return total;
+}
+
 double mul_macs(const Shape& xs, const Shape& ys, const Shape& rs) {
   double total = 1.0;
   for (size_t a = 0; a < rs.size(); a++) {

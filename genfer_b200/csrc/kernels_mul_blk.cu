@@ -334,7 +334,7 @@ bool blk_mul_applicable(const Ctx& ctx, const MulArgs& a) {
   if (!blk_geom(a, &g)) return false;
   u64 slabs = a.row_count;
   for (int d = 1; d < g.na; d++) slabs *= a.rs[d];
-  return slabs >= 64 || (ctx.fast_mul == 2 && slabs >= 1);   // mode 2 forces the kernel (tests)
+  return slabs >= 64 || (slabs >= 1 && (ctx.fast_mul == 2 || args_macs(a) >= DFMA_MIN_MACS));   // mode 2 forces the kernel (tests)
 }
 
 struct BlkItem { unsigned xoff, yoff, zrow, kind, zv; };
@@ -612,7 +612,9 @@ void launch_mul_blk(Ctx& ctx, const MulArgs& a) {
       total_pairs += box;
     }
     u64 slots = (u64)ctx.sm_count * (g.bt == 256 ? 1 : 2);
-    u64 chunk = std::max<u64>(8 * g.G, total_pairs / (slots * 16) + 1);
+    // at least 8 rounds per unit amortise its set-up -- unless that leaves resident-CTA slots empty (mid-size products)
+    const u64 min_chunk = total_pairs >= slots * 8 * (u64)g.G ? 8 * (u64)g.G : (u64)g.G;
+    u64 chunk = std::max<u64>(min_chunk, total_pairs / (slots * 16) + 1);
     chunk = (chunk + g.G - 1) / g.G * g.G;   // whole rounds
     for (u64 s = 0; s < n_slabs; s++) {
       u64 box = boxes[s];

@@ -167,7 +167,16 @@ def test_row_shards_tile_the_product(ctx, n, d, world):
     for r in range(world):
         cnt = len(range(r, d, world))
         out[r::world] = gpu_mul_raw(ctx, x, y, (d,) * n, rows=(r, world, cnt))
-    assert np.array_equal(out.view(np.uint64), full.view(np.uint64))
+    # partial rows meet in HBM through RED.ADD and the units of a row subset split the j box differently from those of the
+    # full product, so shards agree with the full launch to rounding, not bit for bit (the reference-order kernel does)
+    assert rel_err(out, full) <= 1e-13
+    ctx.set_fast_mul(0)
+    full0 = gpu_mul_raw(ctx, x, y, (d,) * n, fast=False)
+    out0 = np.empty_like(full0)
+    for r in range(world):
+        cnt = len(range(r, d, world))
+        out0[r::world] = gpu_mul_raw(ctx, x, y, (d,) * n, rows=(r, world, cnt), fast=False)
+    assert np.array_equal(out0.view(np.uint64), full0.view(np.uint64))
 
 
 def conv1d_trunc(a, b, n):

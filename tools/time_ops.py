@@ -33,7 +33,7 @@ genfer_b200.set_default_context(ctx)
 TP = genfer_b200.TaylorPoly
 
 
-def timed(fns, reps=10, warm=3):
+def timed(fns, reps=10, warm=8):
     """fns: callables run round-robin (different operands, so that reads come from HBM, not L2)."""
     keep = [None] * 3          # results stay alive for three calls: the pool must hand out a different output buffer each
     for i in range(warm):      # time (an output that is overwritten in place every call never leaves the 126 MB L2)
