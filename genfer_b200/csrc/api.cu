@@ -13,7 +13,24 @@ BufP Ctx::alloc(u64 n) {
   b->n = n;
   b->core = core;
   b->owned = true;
+  const double t0 = hist ? now() : 0.0;
   GTP_CUDA(cudaMallocAsync((void**)&b->d, std::max<u64>(n, 1) * sizeof(double), stream));
+  if (hist) t_alloc += now() - t0;
+  if (!fused_cls.empty()) fused_cls.erase(b->d);   // a classification recorded for an earlier tensor at this address is stale
+  return b;
+}
+
+BufP Ctx::alloc_host_visible(const double* vals, int n) {
+  if (!scalars || n > 2) return nullptr;
+  double* slot = scalars->acquire();
+  if (!slot) return nullptr;
+  for (int i = 0; i < n; i++) slot[i] = vals[i];
+  auto b = std::make_shared<Buf>();
+  b->d = slot;
+  b->n = (u64)n;
+  b->owned = false;
+  b->core = core;
+  b->pool = scalars;
   return b;
 }
 
@@ -86,8 +103,13 @@ PolyP from_values(Ctx& c, const Shape& shape, const Shape& degrees, const double
   return p;
 }
 PolyP scalar_poly(Ctx& c, double x, Shape shape_ones, Shape degrees) {
-  PolyP p = new_uninit(c, shape_ones, degrees);
-  launch_fill(c, p->buf->d, 1, x);
+  PolyP p;
+  if (BufP slot = c.alloc_host_visible(&x, 1)) {   // written by the host: no launch
+    p = make_poly(slot, 0, shape_ones, degrees);
+  } else {
+    p = new_uninit(c, shape_ones, degrees);
+    launch_fill(c, p->buf->d, 1, x);
+  }
   p->cls->known = true;
   p->cls->linear = false;
   p->cls->first = x;
@@ -98,11 +120,48 @@ PolyP zero_with(Ctx& c, const Shape& degrees) {  // :208-216
 }
 
 // ---- data-dependent predicates (cached per handle) ----------------------------------------------
+// The producing kernel may already have classified this tensor (fused_cls_begin): wait for its slot instead of launching.
+static bool classify_from_producer(Ctx& c, const gtp_poly& p) {
+  if (c.fused_cls.empty() || p.off != 0) return false;
+  auto it = c.fused_cls.find(p.ptr());
+  if (it == c.fused_cls.end() || it->second.shape != p.shape) return false;
+  const unsigned long long seq = it->second.seq;
+  if (c.cls_seq - seq >= Ctx::CLS_RING) return false;   // the ring has wrapped past this slot
+  const ClsSlot* slot = c.cls_ring + (seq % Ctx::CLS_RING);
+  const double t0 = c.hist ? Ctx::now() : 0.0;
+  for (unsigned long long spins = 0; slot->seq != seq; ++spins) {
+    if (slot->seq > seq) return false;
+    if ((spins & 0xfffff) == 0xfffff) {
+      cudaError_t e = cudaStreamQuery(c.stream);
+      if (e != cudaSuccess && e != cudaErrorNotReady) GTP_CUDA(e);
+      if (e == cudaSuccess && slot->seq != seq) return false;
+    }
+  }
+  if (c.hist) c.t_spin += Ctx::now() - t0;
+  std::atomic_thread_fence(std::memory_order_acquire);
+  p.cls->first = slot->first;
+  p.cls->linear = false;
+  const unsigned viol = slot->viol_mask;
+  for (size_t v = 0; v < p.shape.size(); v++) {
+    if (p.shape[v] < 2) continue;
+    if (!(viol & (1u << v))) {
+      p.cls->linear = true;
+      p.cls->c = p.cls->first;
+      p.cls->m = slot->slope[v];
+      p.cls->v = v;
+      break;
+    }
+  }
+  p.cls->known = true;
+  c.fused_hits++;
+  return true;
+}
 void classify(Ctx& c, const gtp_poly& p) {
   if (p.cls->known) return;
+  if (classify_from_producer(c, p)) return;
   if (p.len() == 1) {
     if (!classify_small_zero_copy(c, p.ptr(), p.shape)) {
-      GTP_CUDA(cudaMemcpyAsync(&c.rb_host->vals[0], p.ptr(), sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+      GTP_CUDA(cudaMemcpyAsync(&c.rb_host->vals[0], p.ptr(), sizeof(double), cudaMemcpyDefault, c.stream));
       c.sync();
     }
     p.cls->first = c.rb_host->vals[0];
@@ -197,12 +256,14 @@ PolyP with_degrees(PolyP p, const Shape& d) {
 }
 
 // element-wise op of a whole tensor against a device scalar
-PolyP ew_scalar(Ctx& c, EwOp op, const gtp_poly& a, const double* s, const Shape& degrees) {
+PolyP ew_scalar(Ctx& c, EwOp op, const gtp_poly& a, const gtp_poly& sp, const Shape& degrees) {
   PolyP r = new_uninit(c, a.shape, degrees);
   EwOperand A;
   A.p = a.ptr();
   A.shape = a.shape;
-  launch_ew(c, op, a.shape, A, nullptr, r->buf->d, a.shape, {}, -1, nullptr, nullptr, s);
+  // a scalar whose value the host already knows (constants, classified handles) travels in the kernel parameters
+  const double* by_value = (sp.cls->known && sp.len() == 1) ? &sp.cls->first : nullptr;
+  launch_ew(c, op, a.shape, A, nullptr, r->buf->d, a.shape, {}, -1, nullptr, nullptr, by_value ? nullptr : sp.ptr(), nullptr, 0, by_value);
   return r;
 }
 
@@ -218,9 +279,9 @@ PolyP poly_add(Ctx& c, const gtp_poly& a0, const gtp_poly& b0, bool subtract) {
   broadcast(a, b);
   PolyP at = truncate_degrees(c, a, rd), bt = truncate_degrees(c, b, rd);
   if (bt->len() == 1)  // `*self.first_mut() (+|-)= other.first()` (:862-865, :919-922)
-    return ew_scalar(c, subtract ? EW_SUB_FIRST : EW_ADD_FIRST, *at, bt->ptr(), rd);
+    return ew_scalar(c, subtract ? EW_SUB_FIRST : EW_ADD_FIRST, *at, *bt, rd);
   if (at->len() == 1)  // (:866-869) / `-(other - self)` (:923-926)
-    return ew_scalar(c, subtract ? EW_RSUB_FIRST : EW_ADD_FIRST, *bt, at->ptr(), rd);
+    return ew_scalar(c, subtract ? EW_RSUB_FIRST : EW_ADD_FIRST, *bt, *at, rd);
   Shape shape = max_shape(*at, *bt);
   PolyP r = new_uninit(c, shape, rd);
   EwOperand A, B;
@@ -272,7 +333,7 @@ PolyP mul_linear(Ctx& c, const gtp_poly& self, double cst, double m, const doubl
     u64 outer = 1, inner = 1;
     for (size_t a = 0; a < v; a++) outer *= shape[a];
     for (size_t a = v + 1; a < shape.size(); a++) inner *= shape[a];
-    launch_mul_linear(c, self.ptr(), r->buf->d, outer, self.shape[v], shape[v], inner, cst, m);
+    launch_mul_linear(c, self.ptr(), r->buf->d, outer, self.shape[v], shape[v], inner, cst, m, shape);
     return r;
   }
   if (cst == 0.0) return mul_var(c, self, m_dev, v, shape, degrees);
@@ -292,8 +353,8 @@ PolyP poly_mul(Ctx& c, const gtp_poly& a0, const gtp_poly& b0) {
   PolyP at = truncate_degrees(c, a, d), bt = truncate_degrees(c, b, d);
   if (is_one(c, *at)) return with_degrees(share(*bt), d);  // :1032-1037
   if (is_one(c, *bt)) return with_degrees(share(*at), d);
-  if (at->len() == 1) return ew_scalar(c, EW_SCALE_DEV, *bt, at->ptr(), d);  // :1040-1043  c * x
-  if (bt->len() == 1) return ew_scalar(c, EW_SCALE_DEV, *at, bt->ptr(), d);  // :1044-1047
+  if (at->len() == 1) return ew_scalar(c, EW_SCALE_DEV, *bt, *at, d);  // :1040-1043  c * x
+  if (bt->len() == 1) return ew_scalar(c, EW_SCALE_DEV, *at, *bt, d);  // :1044-1047
   classify(c, *at);
   if (at->cls->linear) {  // :1052-1056
     u64 v = at->cls->v;
@@ -332,7 +393,7 @@ PolyP poly_div(Ctx& c, const gtp_poly& a0, const gtp_poly& b0, PolyP* recip_cach
   Shape d = min_degrees(a, b);  // after broadcast (:1199-1200)
   PolyP at = truncate_degrees(c, a, d), bt = truncate_degrees(c, b, d);
   if (is_one(c, *bt)) return with_degrees(share(*at), d);                     // :1205-1207
-  if (bt->len() == 1) return ew_scalar(c, EW_DIV_DEV, *at, bt->ptr(), d);     // :1210-1213
+  if (bt->len() == 1) return ew_scalar(c, EW_DIV_DEV, *at, *bt, d);     // :1210-1213
   Shape rs = d;
   int nonunit = 0, axis = -1;
   for (size_t i = 0; i < rs.size(); i++) {
@@ -620,7 +681,7 @@ PolyP slice_scale(Ctx& c, const gtp_poly& a, u64 v, u64 n, int kind) {
   A.p = a.ptr();
   A.shape = a.shape;
   A.lo = lo;
-  double tab[256];
+  double tab[1024];
   if (prod(ext) < (1ull << 32) - 4096 && host_factors(kind, n, ext[v], tab)) {   // one launch: the table rides in the parameters
     launch_ew(c, EW_COPY, ext, A, nullptr, r->buf->d, ext, {}, (int)v, nullptr, nullptr, nullptr, tab, (int)ext[v]);
     return r;
@@ -663,12 +724,17 @@ PolyP poly_subst_var(Ctx& c, const gtp_poly& self, u64 v, const gtp_poly& subst)
     GTP_CHECK(d.size() == self.shape.size(), GTP_ERR_SHAPE, "subst_var: substitution has more variables than self");
     Shape ext(self.shape.size());
     for (size_t a = 0; a < ext.size(); a++) ext[a] = std::min(self.shape[a], d[a]);
-    BufP fac = c.alloc(ext[v]);
-    launch_factors(c, 2, 0, ext[v], subst.ptr() + stride_of(subst.shape, v), fac->d);
     PolyP r = new_uninit(c, ext, d);
     EwOperand A;
     A.p = self.ptr();
     A.shape = self.shape;
+    double tab[1024];
+    if (prod(ext) < (1ull << 32) - 4096 && host_factors(2, 0, ext[v], tab, subst.cls->m)) {   // m is known from the classification
+      launch_ew(c, EW_COPY, ext, A, nullptr, r->buf->d, ext, {}, (int)v, nullptr, nullptr, nullptr, tab, (int)ext[v]);
+      return r;
+    }
+    BufP fac = c.alloc(ext[v]);
+    launch_factors(c, 2, 0, ext[v], subst.ptr() + stride_of(subst.shape, v), fac->d);
     launch_ew(c, EW_COPY, ext, A, nullptr, r->buf->d, ext, {}, (int)v, fac->d);
     return r;
   }
@@ -729,6 +795,8 @@ int gtp_ctx_create(int device, void* cuda_stream, gtp_ctx** out) {
   *out = nullptr;
   static thread_local std::string create_err;
   gtp_ctx* c = new gtp_ctx();
+  if (const char* h = getenv("GTP_LAUNCH_HIST"))
+    if (h[0] == '1') c->hist = new std::map<std::string, u64>();
   int rc = wrap(c, [&] {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -747,6 +815,25 @@ int gtp_ctx_create(int device, void* cuda_stream, gtp_ctx** out) {
       c->core->own = true;
     }
     c->stream = c->core->stream;
+    if (!(getenv("GTP_NO_FUSED_CLS") && getenv("GTP_NO_FUSED_CLS")[0] == '1')) {
+      ClsSlot* ring = nullptr;
+      if (cudaHostAlloc((void**)&ring, sizeof(ClsSlot) * Ctx::CLS_RING, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) {
+        void* dp = nullptr;
+        if (cudaHostGetDevicePointer(&dp, ring, 0) == cudaSuccess && dp == (void*)ring) {
+          memset(ring, 0, sizeof(ClsSlot) * Ctx::CLS_RING);
+          c->cls_ring = ring;
+        } else {
+          cudaGetLastError();
+          cudaFreeHost(ring);
+        }
+      } else {
+        cudaGetLastError();
+      }
+    }
+    if (!(getenv("GTP_NO_SCALAR_POOL") && getenv("GTP_NO_SCALAR_POOL")[0] == '1')) {
+      c->scalars = std::make_shared<ScalarPool>();
+      c->scalars->core = c->core;
+    }
     cudaDeviceProp prop;
     GTP_CUDA(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
@@ -777,6 +864,13 @@ void gtp_ctx_destroy(gtp_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  if (c->hist) {
+    fprintf(stderr, "[gtp launches] %10llu  classifications served by the producing kernel\n", (unsigned long long)c->fused_hits);
+    fprintf(stderr, "[gtp host time] launch calls %.3f s, cudaMallocAsync %.3f s, waiting for producer classifications %.3f s\n", c->t_launch, c->t_alloc, c->t_spin);
+    for (auto& kv : *c->hist) fprintf(stderr, "[gtp launches] %10llu  %s\n", (unsigned long long)kv.second, kv.first.c_str());
+    delete c->hist;
+  }
+  if (c->cls_ring) cudaFreeHost(c->cls_ring);
   if (c->rb_host) cudaFreeHost(c->rb_host);
   if (c->rb_dev) cudaFree(c->rb_dev);
   if (c->gather_host) cudaFreeHost(c->gather_host);
@@ -818,7 +912,7 @@ int gtp_from_device(gtp_ctx* c, int ndim, const uint64_t* shape, const uint64_t*
 int gtp_to_host(gtp_ctx* c, const gtp_poly* p, double* out) {
   return wrap(c, [&] {
     GTP_CHECK(p && out, GTP_ERR_ARG, "null argument");
-    GTP_CUDA(cudaMemcpyAsync(out, p->ptr(), p->len() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    GTP_CUDA(cudaMemcpyAsync(out, p->ptr(), p->len() * sizeof(double), cudaMemcpyDefault, c->stream));   // scalar-pool slots are host memory
     c->sync();
   });
 }
@@ -853,7 +947,9 @@ static PolyP make_var(Ctx& c, u64 v, double x, u64 stored, bool one_coeff, Shape
   Shape shape(degrees.size(), 1);
   shape[v] = stored;
   double vals[2] = {x, one_coeff ? 1.0 : 0.0};
-  PolyP p = from_values(c, shape, degrees, vals);
+  PolyP p;
+  if (BufP slot = c.alloc_host_visible(vals, (int)stored)) p = make_poly(slot, 0, shape, degrees);
+  else p = from_values(c, shape, degrees, vals);
   p->cls->known = true;
   p->cls->first = x;
   p->cls->linear = stored >= 2;  // [x, m] along v, every other entry absent
@@ -1023,7 +1119,7 @@ int gtp_constant_term(gtp_ctx* c, const gtp_poly* a, double* out) {  // :296-299
       *out = a->cls->first;
       return;
     }
-    GTP_CUDA(cudaMemcpyAsync(&c->rb_host->vals[0], a->ptr(), sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    GTP_CUDA(cudaMemcpyAsync(&c->rb_host->vals[0], a->ptr(), sizeof(double), cudaMemcpyDefault, c->stream));
     c->sync();
     *out = c->rb_host->vals[0];
   });
@@ -1044,7 +1140,7 @@ int gtp_coefficient(gtp_ctx* c, const gtp_poly* a, const uint64_t* index, int n_
       }
     }
     GTP_CHECK((size_t)n_index >= a->shape.size(), GTP_ERR_INDEX, "index is too short");
-    GTP_CUDA(cudaMemcpyAsync(&c->rb_host->vals[0], a->ptr() + off, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    GTP_CUDA(cudaMemcpyAsync(&c->rb_host->vals[0], a->ptr() + off, sizeof(double), cudaMemcpyDefault, c->stream));
     c->sync();
     *out = c->rb_host->vals[0];
   });

@@ -3,6 +3,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
+#include <map>
+#include <unordered_map>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -54,14 +57,63 @@ struct StreamCore {
   }
 };
 
+// Slots of two doubles in mapped pinned host memory for scalars and `x + eps_v` variables (the tensors of one or two
+// coefficients every program creates by the hundred thousand: constants, probabilities, variables).  The host writes the
+// value directly -- no kernel launch, no copy -- and kernels read it over PCIe through the same (unified) address.  A
+// released slot may still be read by kernels in flight, so it is recycled only after a stream synchronise, which happens
+// once per ~10^6 releases.
+struct ScalarPool {
+  static constexpr size_t SLOTS_PER_BLOCK = 1 << 16, MAX_BLOCKS = 16;
+  std::shared_ptr<StreamCore> core;
+  std::vector<double*> blocks, free_slots, pending;
+  bool disabled = false;
+  double* acquire() {
+    if (disabled) return nullptr;
+    if (free_slots.empty()) {
+      if (blocks.size() < MAX_BLOCKS || pending.empty()) {
+        double* b = nullptr;
+        if (cudaHostAlloc((void**)&b, SLOTS_PER_BLOCK * 16, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+          cudaGetLastError();
+          disabled = blocks.empty();
+          if (disabled || pending.empty()) return nullptr;
+        } else {
+          void* dp = nullptr;
+          if (cudaHostGetDevicePointer(&dp, b, 0) != cudaSuccess || dp != (void*)b) {   // no unified addressing
+            cudaGetLastError();
+            cudaFreeHost(b);
+            disabled = true;
+            return nullptr;
+          }
+          blocks.push_back(b);
+          for (size_t i = SLOTS_PER_BLOCK; i-- > 0;) free_slots.push_back(b + 2 * i);
+        }
+      }
+      if (free_slots.empty()) {
+        if (cudaStreamSynchronize(core->stream) != cudaSuccess) return nullptr;
+        free_slots.swap(pending);
+      }
+    }
+    double* p = free_slots.back();
+    free_slots.pop_back();
+    return p;
+  }
+  void release(double* p) { pending.push_back(p); }
+  ~ScalarPool() {
+    if (core && core->stream) cudaStreamSynchronize(core->stream);
+    for (double* b : blocks) cudaFreeHost(b);
+  }
+};
+
 // Immutable device buffer.  Freed stream-ordered (cudaFreeAsync) when the last handle drops it.
 struct Buf {
   double* d = nullptr;
   u64 n = 0;       // doubles
   bool owned = true;
   std::shared_ptr<StreamCore> core;
+  std::shared_ptr<ScalarPool> pool;   // set: `d` is a slot of the scalar pool (host-visible)
   ~Buf() {
-    if (owned && d && core) cudaFreeAsync(d, core->stream);
+    if (pool) pool->release(d);
+    else if (owned && d && core) cudaFreeAsync(d, core->stream);
   }
 };
 using BufP = std::shared_ptr<Buf>;
@@ -72,6 +124,20 @@ struct Readback {
   unsigned int flag;       // generic boolean result (eq / any)
   double vals[64];         // c, m, sums, gathered scalars ...
   volatile unsigned long long seq;  // written LAST by the single-CTA classify kernel (zero-copy path): host spins on it
+};
+
+// Classification written by the PRODUCING kernel (single-CTA element-wise kernels run the extract_linear scan over
+// their own output as an epilogue): one slot of a ring in mapped pinned memory per fused launch.  `seq` is written last.
+struct ClsSlot {
+  double first;                    // coeffs.first()
+  double slope[GTP_MAX_NDIM];      // candidate m of axis v (the coefficient at e_v)
+  unsigned viol_mask;              // bit v set <=> axis v is NOT a linear axis
+  unsigned pad;
+  volatile unsigned long long seq;
+};
+struct FusedCls {
+  unsigned long long seq = 0;
+  Shape shape;
 };
 
 struct Ctx {
@@ -86,6 +152,7 @@ struct Ctx {
   double* gather_host = nullptr;        // pinned, for gtp_gather_axis / to_host staging
   u64 gather_cap = 0;
   u64 launches = 0;
+  std::map<std::string, u64>* hist = nullptr;   // per-kernel launch counts (GTP_LAUNCH_HIST=1; printed when the context is destroyed)
   u64 rb_seq = 0;               // sequence number of the last zero-copy read-back request
   Readback* rb_host_dev = nullptr;  // device alias of rb_host (mapped pinned memory)
   int fast_mul = 1;  // 0: reference-order kernel only, 1: auto, 2: force the blocked kernel even on tiny products (tests)
@@ -97,7 +164,16 @@ struct Ctx {
   bool blk_octet = false;            // experimental octet tables for single-plane slabs (8 staged pairs = 8 lanes)
   bool blk_fold_tables = true;       // structured (folded) item tables for dense cube slabs; false: evenly dealt
 
+  std::shared_ptr<ScalarPool> scalars;   // created with the context
+  static constexpr unsigned CLS_RING = 1 << 16;
+  ClsSlot* cls_ring = nullptr;           // mapped pinned (host pointer == device pointer), CLS_RING slots
+  unsigned long long cls_seq = 0;        // last sequence number handed to a fused launch (slot = seq % CLS_RING)
+  std::unordered_map<const double*, FusedCls> fused_cls;   // result buffer -> its in-flight / finished classification
+  u64 fused_hits = 0;
+  double t_spin = 0, t_alloc = 0, t_launch = 0;   // seconds, only measured when `hist` is on (GTP_LAUNCH_HIST=1)
+  static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
   BufP alloc(u64 n_doubles);
+  BufP alloc_host_visible(const double* vals, int n);   // n <= 2: a scalar-pool slot holding vals (nullptr: pool unavailable)
   void sync() { GTP_CUDA(cudaStreamSynchronize(stream)); }
 };
 

@@ -8,8 +8,13 @@ constexpr int MAXD = GTP_MAX_NDIM;
 
 #define GTP_LAUNCH(ctx, kernel, grid, block, smem, ...)                         \
   do {                                                                          \
+    const double _t0 = (ctx).hist ? ::gtp::Ctx::now() : 0.0;                    \
     kernel<<<(grid), (block), (smem), (ctx).stream>>>(__VA_ARGS__);             \
     (ctx).launches++;                                                           \
+    if ((ctx).hist) {                                                           \
+      (*(ctx).hist)[#kernel]++;                                                 \
+      (ctx).t_launch += ::gtp::Ctx::now() - _t0;                                \
+    }                                                                           \
     GTP_CUDA(cudaGetLastError());                                               \
   } while (0)
 
@@ -31,6 +36,61 @@ enum EwOp : int {
   EW_RSUB_FIRST = 9,   // out = -(idx==0 ? a - *s : a)       (Sub scalar self   :923-926)
 };
 
+// extract_linear scan (:275-294) over a dense tensor
+struct ClsParams {
+  int ndim;
+  unsigned shape[MAXD];
+  long long str[MAXD];
+  u64 total;
+  unsigned all_mask;
+};
+// One CTA classifies the dense tensor `in` it has just written (call after the last store; contains the barriers)
+// and publishes the result in `slot`, sequence number last.
+__device__ __forceinline__ void cls_epilogue(const double* in, const ClsParams& p, ClsSlot* slot, unsigned long long seq) {
+  __shared__ unsigned cls_sh_mask;
+  __syncthreads();                 // the CTA's own stores are visible to all its threads after the barrier
+  if (threadIdx.x == 0) cls_sh_mask = 0;
+  __syncthreads();
+  unsigned mask = 0;
+  for (unsigned lin = threadIdx.x; lin < (unsigned)p.total; lin += blockDim.x) {
+    const double x = in[lin];
+    if (x != 0.0) {
+      unsigned rem = lin;
+      int nz_axis = -1, nz_count = 0;
+      unsigned nz_val = 0;
+      for (int d = p.ndim - 1; d >= 0; --d) {
+        const unsigned q = rem / p.shape[d], i = rem - q * p.shape[d];
+        rem = q;
+        if (i != 0) {
+          nz_count++;
+          nz_axis = d;
+          nz_val = i;
+        }
+      }
+      if (nz_count >= 2) mask |= p.all_mask;
+      else if (nz_count == 1) mask |= (nz_val >= 2) ? p.all_mask : (p.all_mask & ~(1u << nz_axis));
+    }
+  }
+  if (mask) atomicOr(&cls_sh_mask, mask);
+  __syncthreads();
+  if ((int)threadIdx.x < p.ndim) slot->slope[threadIdx.x] = p.shape[threadIdx.x] >= 2 ? in[p.str[threadIdx.x]] : 0.0;
+  if (threadIdx.x == 0) {
+    slot->first = in[0];
+    slot->viol_mask = cls_sh_mask;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) slot->seq = seq;
+}
+struct FusedClsArgs {   // kernel-side half of a fused classification (slot == nullptr: none)
+  ClsSlot* slot;
+  unsigned long long seq;
+  ClsParams p;
+};
+// Host: should the single-CTA launch that writes the whole dense tensor `out` (shape) classify it?  Fills `f` and
+// registers the pending result under `out`; classify() (api.cu) picks it up.
+bool fused_cls_begin(Ctx& ctx, const double* out, const Shape& shape, FusedClsArgs* f);
+
 struct EwParams {
   int ndim;
   int fax;            // axis the factor / keep arrays are indexed by (box coordinates)
@@ -44,7 +104,9 @@ struct EwParams {
   double* out;
   const double* fac;            // device array (EW_COPY) or nullptr
   const unsigned char* keep;    // device array (EW_MASK)
-  const double* s;              // device scalar
+  const double* s;              // device scalar, or nullptr: the scalar is s_val
+  double s_val;
+  FusedClsArgs cls;             // epilogue classification of the (whole, dense) output by a single-CTA launch
 };
 
 // High-level description of one operand for the host-side coalescer.
@@ -57,13 +119,15 @@ struct EwOperand {
 void launch_ew(Ctx& ctx, EwOp op, const Shape& box, const EwOperand& a, const EwOperand* b,
                double* out, const Shape& out_shape, const Shape& out_lo, int fax = -1,
                const double* fac = nullptr, const unsigned char* keep = nullptr, const double* s = nullptr,
-               const double* host_tab = nullptr, int host_tab_len = 0);   // host_tab: factor table by kernel parameter
-// derivative / binomial factor tables of at most 256 entries built on the host (kinds 0 and 1 of launch_factors)
-bool host_factors(int kind, u64 n, u64 len, double* fac);
+               const double* host_tab = nullptr, int host_tab_len = 0,   // host_tab: factor table by kernel parameter
+               const double* s_host = nullptr);                           // scalar by value (instead of `s`)
+// derivative / binomial factor tables of at most 1024 entries built on the host (kinds 0 and 1 of launch_factors)
+bool host_factors(int kind, u64 n, u64 len, double* fac, double m = 0.0);   // kind 2: powers of m
 
 void launch_fill(Ctx& ctx, double* dst, u64 n, double value);
 // fused mul_linear / mul_var (:589-623) on the (outer, xlen, inner) view of the variable's axis; out has olen (xlen or xlen + 1) slices
-void launch_mul_linear(Ctx& ctx, const double* x, double* out, u64 outer, u64 xlen, u64 olen, u64 inner, double c, double m);
+void launch_mul_linear(Ctx& ctx, const double* x, double* out, u64 outer, u64 xlen, u64 olen, u64 inner, double c, double m,
+                       const Shape& out_shape);
 // fac[k], k < len:  kind 0: falling factorials (n+k)!/k!  (derivative :472-479)
 //                   kind 1: binomials C(n+k,k)            (taylor_expansion_of_coeff :499-507)
 //                   kind 2: powers (*m)^k                 (subst_var linear path :557-565)

@@ -32,6 +32,8 @@ __global__ void __launch_bounds__(256) k_ew(const EwParams p) {
       if (d == p.fax) fidx = i;
     }
     double r;
+    const double sv = (OP == EW_SCALE_DEV || OP == EW_DIV_DEV || OP == EW_ADD_FIRST || OP == EW_SUB_FIRST || OP == EW_RSUB_FIRST)
+                          ? (p.s ? *p.s : p.s_val) : 0.0;
     if (OP == EW_COPY) {
       double a = p.a[ao];
       r = p.fac ? __dmul_rn(a, p.fac[fidx]) : a;
@@ -42,17 +44,17 @@ __global__ void __launch_bounds__(256) k_ew(const EwParams p) {
     } else if (OP == EW_MASK) {
       r = p.keep[fidx] ? p.a[ao] : 0.0;
     } else if (OP == EW_SCALE_DEV) {
-      r = __dmul_rn(*p.s, p.a[ao]);
+      r = __dmul_rn(sv, p.a[ao]);
     } else if (OP == EW_DIV_DEV) {
-      r = __ddiv_rn(p.a[ao], *p.s);
+      r = __ddiv_rn(p.a[ao], sv);
     } else if (OP == EW_NEG) {
       r = -p.a[ao];
     } else if (OP == EW_ADD_FIRST) {
-      r = first ? __dadd_rn(p.a[ao], *p.s) : p.a[ao];
+      r = first ? __dadd_rn(p.a[ao], sv) : p.a[ao];
     } else if (OP == EW_SUB_FIRST) {
-      r = first ? __dsub_rn(p.a[ao], *p.s) : p.a[ao];
+      r = first ? __dsub_rn(p.a[ao], sv) : p.a[ao];
     } else {  // EW_RSUB_FIRST
-      r = -(first ? __dsub_rn(p.a[ao], *p.s) : p.a[ao]);
+      r = -(first ? __dsub_rn(p.a[ao], sv) : p.a[ao]);
     }
     p.out[oo] = r;
   }
@@ -64,8 +66,9 @@ __global__ void __launch_bounds__(256) k_ew(const EwParams p) {
 // and 16-byte aligned in every tensor (VEC2) -- 16-byte loads and stores.  `tab` is a factor table passed in the
 // kernel parameters (host-built derivative / binomial factors: no table-building launch); fac == nullptr, tab == nullptr:
 // no factor.  Arithmetic is identical to k_ew.
+constexpr int FAC_TAB = 1024;   // 8 KB of kernel parameters (large parameter space, CUDA >= 12.1)
 struct FacTab {
-  double f[256];
+  double f[FAC_TAB];
 };
 template <int OP, bool VEC2>
 __device__ __forceinline__ void ew_fast_body(const EwParams& p, const double* __restrict__ fac) {
@@ -116,7 +119,7 @@ __device__ __forceinline__ void ew_fast_body(const EwParams& p, const double* __
       }
     }
     double sv = 0.0;
-    if (OP == EW_SCALE_DEV || OP == EW_DIV_DEV || OP == EW_ADD_FIRST || OP == EW_SUB_FIRST || OP == EW_RSUB_FIRST) sv = *p.s;
+    if (OP == EW_SCALE_DEV || OP == EW_DIV_DEV || OP == EW_ADD_FIRST || OP == EW_SUB_FIRST || OP == EW_RSUB_FIRST) sv = p.s ? *p.s : p.s_val;
 #pragma unroll
     for (int j = 0; j < U; j++) {
       if (!live[j]) continue;
@@ -160,14 +163,40 @@ __device__ __forceinline__ void ew_fast_body(const EwParams& p, const double* __
 template <int OP, bool VEC2>
 __global__ void __launch_bounds__(256) k_ew_fast(const __grid_constant__ EwParams p) {
   ew_fast_body<OP, VEC2>(p, p.fac);
+  if (p.cls.slot) cls_epilogue(p.out, p.cls.p, p.cls.slot, p.cls.seq);   // gridDim.x == 1 (launch_ew)
 }
 template <bool VEC2>
 __global__ void __launch_bounds__(256) k_ew_tab(const __grid_constant__ EwParams p, const __grid_constant__ FacTab tab) {
   // staged in shared memory: a warp's lanes index the table with different k, and divergent constant-bank reads serialise
-  __shared__ double sfac[256];
-  sfac[threadIdx.x] = tab.f[threadIdx.x];
+  __shared__ double sfac[FAC_TAB];
+  for (int i = threadIdx.x; i < FAC_TAB; i += blockDim.x) sfac[i] = tab.f[i];
   __syncthreads();
   ew_fast_body<EW_COPY, VEC2>(p, sfac);
+  if (p.cls.slot) cls_epilogue(p.out, p.cls.p, p.cls.slot, p.cls.seq);
+}
+
+bool fused_cls_begin(Ctx& ctx, const double* out, const Shape& shape, FusedClsArgs* f) {
+  f->slot = nullptr;
+  const u64 total = prod(shape);
+  if (!ctx.cls_ring || total == 0 || total > 1024 || shape.size() > (size_t)MAXD) return false;
+  const unsigned long long seq = ++ctx.cls_seq;
+  f->slot = ctx.cls_ring + (seq % Ctx::CLS_RING);
+  f->seq = seq;
+  ClsParams& p = f->p;
+  memset(&p, 0, sizeof(p));
+  p.ndim = (int)shape.size();
+  p.total = total;
+  long long st = 1;
+  for (int d = p.ndim - 1; d >= 0; --d) {
+    p.shape[d] = (unsigned)shape[d];
+    p.str[d] = st;
+    st *= (long long)shape[d];
+  }
+  p.all_mask = p.ndim >= 32 ? 0xffffffffu : ((1u << p.ndim) - 1u);
+  FusedCls& e = ctx.fused_cls[out];
+  e.seq = seq;
+  e.shape = shape;
+  return true;
 }
 
 static Shape strides_of(const Shape& shape) {
@@ -178,7 +207,7 @@ static Shape strides_of(const Shape& shape) {
 
 void launch_ew(Ctx& ctx, EwOp op, const Shape& box, const EwOperand& a, const EwOperand* b, double* out,
                const Shape& out_shape, const Shape& out_lo, int fax, const double* fac,
-               const unsigned char* keep, const double* s, const double* tab, int tab_len) {
+               const unsigned char* keep, const double* s, const double* tab, int tab_len, const double* s_host) {
   const int nd = (int)box.size();
   GTP_CHECK(nd <= MAXD, GTP_ERR_ARG, "ndim exceeds GTP_MAX_NDIM");
   u64 total = prod(box);
@@ -249,7 +278,8 @@ void launch_ew(Ctx& ctx, EwOp op, const Shape& box, const EwOperand& a, const Ew
   p.out = out;
   p.fac = fac;
   p.keep = keep;
-  p.s = s;
+  p.s = s_host ? nullptr : s;
+  p.s_val = s_host ? *s_host : 0.0;
   int block = 256;
   if (total < (1ull << 32) - 4096) {
     // innermost axis contiguous, even and 16-byte aligned everywhere: element pairs
@@ -269,6 +299,9 @@ void launch_ew(Ctx& ctx, EwOp op, const Shape& box, const EwOperand& a, const Ew
     }
     const u64 units = p.total;
     int grid = (int)std::max<u64>(1, std::min<u64>((units + block * 4 - 1) / (block * 4), (u64)ctx.sm_count * 16));
+    bool whole = box == out_shape;
+    for (u64 l0 : out_lo) whole = whole && l0 == 0;
+    if (whole && grid == 1) fused_cls_begin(ctx, out, out_shape, &p.cls);   // the producer classifies its own output
     if (op == EW_COPY && tab) {
       FacTab t;
       memcpy(t.f, tab, sizeof(double) * tab_len);
@@ -297,8 +330,16 @@ void launch_ew(Ctx& ctx, EwOp op, const Shape& box, const EwOperand& a, const Ew
 
 // Host-built factor tables (plain IEEE double multiplications and divisions in the reference's incremental order, so
 // bit-identical to k_factors): up to 256 entries travel in the kernel parameters.
-bool host_factors(int kind, u64 n, u64 len, double* fac) {
-  if (len > 256 || kind > 1) return false;
+bool host_factors(int kind, u64 n, u64 len, double* fac, double m) {
+  if (len > (u64)FAC_TAB || kind > 2) return false;
+  if (kind == 2) {  // powers m^k (:557-565)
+    volatile double f = 1.0;
+    for (u64 k = 0; k < len; k++) {
+      fac[k] = f;
+      f = f * m;
+    }
+    return true;
+  }
   if (kind == 0) {  // derivative :472-479
     volatile double ff = 1.0;
     for (u64 i = 1; i <= n; i++) ff = ff * (double)(unsigned)i;
@@ -328,7 +369,8 @@ bool host_factors(int kind, u64 n, u64 len, double* fac) {
 // four more passes over HBM); x[.,k-1,.] is re-read from L1/L2.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_mul_linear(const double* __restrict__ x, double* __restrict__ out, unsigned total,
-                                                   unsigned xlen, unsigned olen, unsigned inner, double c, double m, int var_only) {
+                                                   unsigned xlen, unsigned olen, unsigned inner, double c, double m, int var_only,
+                                                   const __grid_constant__ FusedClsArgs cls) {
   constexpr int U = 4;
   const unsigned step = blockDim.x * U;
   for (unsigned base = blockIdx.x * step + threadIdx.x; base < total; base += gridDim.x * step) {
@@ -362,13 +404,18 @@ __global__ void __launch_bounds__(256) k_mul_linear(const double* __restrict__ x
       out[lin] = r;
     }
   }
+  if (cls.slot) cls_epilogue(out, cls.p, cls.slot, cls.seq);
 }
-void launch_mul_linear(Ctx& ctx, const double* x, double* out, u64 outer, u64 xlen, u64 olen, u64 inner, double c, double m) {
+void launch_mul_linear(Ctx& ctx, const double* x, double* out, u64 outer, u64 xlen, u64 olen, u64 inner, double c, double m,
+                       const Shape& out_shape) {
   const u64 total = outer * olen * inner;
   if (total == 0) return;
   int grid = (int)std::max<u64>(1, std::min<u64>((total + 1023) / 1024, (u64)ctx.sm_count * 16));
+  FusedClsArgs cls;
+  cls.slot = nullptr;
+  if (grid == 1) fused_cls_begin(ctx, out, out_shape, &cls);
   GTP_LAUNCH(ctx, k_mul_linear, grid, 256, 0, x, out, (unsigned)total, (unsigned)xlen, (unsigned)olen, (unsigned)inner, c, m,
-             c == 0.0 ? 1 : 0);
+             c == 0.0 ? 1 : 0, cls);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -618,13 +665,6 @@ void launch_sum_all(Ctx& ctx, const double* in, u64 n, double* out_dev) {
 // idx[v] <= 1.  One pass builds the OR of the per-element "ruled out" masks; blocks stop early
 // once every axis is ruled out (dense operands bail out after their first tile).
 // ------------------------------------------------------------------------------------------
-struct ClsParams {
-  int ndim;
-  unsigned shape[MAXD];
-  long long str[MAXD];
-  u64 total;
-  unsigned all_mask;
-};
 __global__ void __launch_bounds__(256) k_classify(const double* __restrict__ in, const ClsParams p, Readback* rb) {
   __shared__ unsigned sh_mask, sh_global;
   if (threadIdx.x == 0) sh_mask = 0;

@@ -10,9 +10,13 @@ import genfer_b200
 from oracle import oracle as O
 
 args = sys.argv[1:]
-reps = 3
-if args and args[0] == "--reps":
-    reps = int(args[1]); args = args[2:]
+reps, cpu_reps = 3, 2
+while args and args[0] in ("--reps", "--cpu-reps"):
+    if args[0] == "--reps":
+        reps = int(args[1])
+    else:
+        cpu_reps = int(args[1])
+    args = args[2:]
 ctx = genfer_b200.Context(0)
 for a in args:
     path, _, lim = a.partition(":")
@@ -25,7 +29,7 @@ for a in args:
         l0 = ctx.launch_count
         t = time.perf_counter(); g = genfer_b200.run_sgcl(src, ctx=ctx, **kw); tg.append(time.perf_counter() - t)
         launches = ctx.launch_count - l0
-    for _ in range(max(1, min(reps, 2))):
+    for _ in range(max(1, min(reps, cpu_reps))):
         t = time.perf_counter(); o = O.run_sgcl(src, **kw); to.append(time.perf_counter() - t)
     rel = abs(g.total - o.total) / abs(o.total) if o.total else abs(g.total)
     print(json.dumps({"program": os.path.relpath(path), "limit": limit, "gpu_s": round(min(tg), 4), "cpu_oracle_s": round(min(to), 4),
