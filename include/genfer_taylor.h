@@ -63,9 +63,14 @@ int gtp_ctx_synchronize(gtp_ctx* ctx);
 void* gtp_ctx_stream(gtp_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t gtp_ctx_launch_count(gtp_ctx* ctx);
-/* tuning knob: 0 = always use the reference-order product kernel (bit-exact), 1 = pick the fastest
- * applicable kernel (default), 2 = use the blocked DFMA kernel even for tiny products (tests);
- * +4 = evenly dealt instead of folded item tables (A/B measurements) */
+/* tuning knob: 0 = always use the reference-order product kernel and the wavefront division (exact order),
+ * 1 = pick the fastest applicable kernel (default: DFMA kernels from 2^20 MACs), 2 = use the DFMA kernels even for
+ * tiny products (tests).  A/B bits: +4 evenly dealt instead of folded item tables (blocked kernel), +8 octet tables
+ * (experimental), +16 sliding kernel off, +32 / +64 force the plane-tiled sliding plan with 4 / 8 planes per slab,
+ * +128 mul_linear as the reference's composition instead of the one-pass kernel.
+ * Environment (read at gtp_ctx_create): GTP_LAUNCH_HIST=1 prints per-kernel launch counts and host-time shares when the
+ * context is destroyed; GTP_NO_SCALAR_POOL=1 / GTP_NO_FUSED_CLS=1 switch the host-written scalar slots / the fused
+ * classification off. */
 int gtp_ctx_set_fast_mul(gtp_ctx* ctx, int enabled);
 
 /* ---- construction, transfer, metadata ------------------------------------------------------- */
