@@ -443,3 +443,76 @@ def test_python_scalar_operands_stay_alive(G):
         assert_same(g + 2.0, o + O().TaylorPoly.from_scalar(2.0))
         assert_same(g - 0.5, o - O().TaylorPoly.from_scalar(0.5))
         assert_same(g / 4.0, o / O().TaylorPoly.from_scalar(4.0))
+
+
+# ---------------------------------------------------------------------------------------------
+# edge cases: 0-d scalars, many variables with unit axes, the maximum rank, IEEE specials
+# ---------------------------------------------------------------------------------------------
+def same_with_nans(g, o):
+    assert_meta_equal(g, o)
+    ga, oa = g.array(), o.array()
+    assert np.array_equal(np.isnan(ga), np.isnan(oa)), f"\n gpu={ga}\n ref={oa}"
+    ok = ~np.isnan(oa)
+    assert np.array_equal(ga[ok].view(np.uint64), oa[ok].view(np.uint64)), f"\n gpu={ga}\n ref={oa}"
+
+
+def test_scalar_polynomials_every_operator(G):
+    """0-dimensional operands (TaylorPoly::from(c), :626-630) through every operator."""
+    for x, y in ((2.5, -0.75), (0.0, 3.0), (1.0, 1.0), (-0.0, 2.0)):
+        gx, ox = G.TaylorPoly.from_scalar(x), O().TaylorPoly.from_scalar(x)
+        gy, oy = G.TaylorPoly.from_scalar(y), O().TaylorPoly.from_scalar(y)
+        for f in (lambda a, b: a + b, lambda a, b: a - b, lambda a, b: a * b, lambda a, b: a / b, lambda a, b: -a,
+                  lambda a, b: a.pow(3), lambda a, b: (a * a + b * b).exp(), lambda a, b: (a * a + b * b).log()):
+            g, o = f(gx, gy), f(ox, oy)
+            assert_meta_equal(g, o)
+            assert_close(g, o)
+        assert gx.is_zero() == ox.is_zero() and gx.is_one() == ox.is_one()
+        assert gx.extract_constant() == x and ox.constant_term() == x
+
+
+def test_many_variables_with_unit_axes(G):
+    """Ten program variables, most axes of stored length 1 (the compact supports of the prodigy programs)."""
+    rng = np.random.default_rng(10)
+    shape = (2, 1, 3, 1, 1, 2, 1, 1, 1, 2)
+    deg = (3, 2, 3, 4, 1, 2, 5, 1, 2, 3)
+    a, b = rng.standard_normal(shape), rng.standard_normal(shape)
+    (ga, oa), (gb, ob) = both(G, a, deg), both(G, b, deg)
+    assert_same(ga + gb, oa + ob)
+    assert_same(ga - gb, oa - ob)
+    assert_same(ga * gb, oa * ob)
+    assert_same(ga.derivative(2, 1), oa.derivative(2, 1))
+    assert_same(ga.shift_down(9, 1), oa.shift_down(9, 1))
+    assert_same(ga.shift_down(0, 1), oa.shift_down(0, 1))
+    assert_same(ga.coefficients_of_term(5, 1), oa.coefficients_of_term(5, 1))
+    assert_same(ga.taylor_expansion_of_coeff(2, 2), oa.taylor_expansion_of_coeff(2, 2))
+    assert_close(ga * gb * ga, oa * ob * oa)
+
+
+def test_maximum_rank(G):
+    """GTP_MAX_NDIM = 24 variables (two non-unit axes)."""
+    shape = [1] * 24
+    shape[3], shape[23] = 3, 4
+    rng = np.random.default_rng(24)
+    a, b = rng.standard_normal(shape), rng.standard_normal(shape)
+    (ga, oa), (gb, ob) = both(G, a), both(G, b)
+    assert_same(ga + gb, oa + ob)
+    assert_same(ga * gb, oa * ob)
+    assert_same(ga.derivative(23, 2), oa.derivative(23, 2))
+    assert_same(ga.shift_down(3, 1), oa.shift_down(3, 1))
+
+
+def test_division_by_zero_constant_term_propagates_ieee_specials(G):
+    """:1167 -- plain f64 division: a divisor series with zero constant term yields inf / NaN, no trap, no error."""
+    a = np.array([[1.0, 2.0, 3.0], [4.0, 5.0, 6.0]])
+    for b in (np.array([[0.0, 1.0, 0.0]]), np.array([[0.0]]), np.array([[0.0, 1.0], [2.0, 0.0]])):
+        (ga, oa), (gb, ob) = both(G, a, (2, 3)), both(G, b, (2, 3))
+        if b.shape == (2, 2):   # general N-D path: compare the exact-order kernels
+            G.default_context().set_fast_mul(0)
+        try:
+            same_with_nans(ga / gb, oa / ob)
+        finally:
+            G.default_context().set_fast_mul(1)
+    big = np.array([1e308, 1e308, 1.0])
+    (gx, ox) = both(G, big)
+    same_with_nans(gx * gx, ox * ox)            # overflow to +inf
+    same_with_nans((gx * gx) - (gx * gx), (ox * ox) - (ox * ox))   # inf - inf = NaN
