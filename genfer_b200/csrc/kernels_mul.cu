@@ -7,6 +7,8 @@
 // summed from zero and then added (mul_1d :972-982 feeding `*z += o` :998) -- so its results are
 // bit-identical to the reference f64 path.  The register-blocked DFMA kernel lives in kernels_mul_blk.cu;
 // launch_mul() picks between them.
+#include <algorithm>
+
 #include "kernels.cuh"
 
 namespace gtp {
@@ -139,6 +141,7 @@ void launch_mul_slide(Ctx& ctx, const MulArgs& a);
 int mul_kernel_kind(const Ctx& ctx, const MulArgs& a) {
   if (!ctx.fast_mul) return 0;
   if ((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.y)) & 15u) return 0;  // cp.async 16-byte staging
+  if (ctx.use_stencil && std::min(prod(a.xs), prod(a.ys)) <= (u64)32 && std::max(prod(a.xs), prod(a.ys)) >= 4096) return 0;  // stencil kernel
   if (ctx.use_slide && slide_mul_applicable(ctx, a)) return 3;
   return blk_mul_applicable(ctx, a) ? 2 : 0;
 }
@@ -197,6 +200,172 @@ static void launch_mul_ordered(Ctx& ctx, const MulArgs& a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Stencil product: one operand has at most ST_MAXT coefficients (the multilinear substitutions and thinning
+// factors of real programs: X of shape [297, 282, 297] times Y of shape [2, 1, 2] is the typical heavy product of the
+// population models).  Such a product is HBM-bound -- a few MACs per output -- and the generic reference-order kernel
+// (64-bit odometers, one dependent gather per MAC) reaches ~0.4 TB/s on it.  Here the small operand's coefficients and
+// their offsets sit in the kernel parameters / registers; a thread computes one output coefficient with 32-bit index
+// arithmetic, its few loads independent of each other.  The terms are visited in the reference's order (outer axes
+// ascending in the X index; the innermost non-unit axis summed from zero and then added, :996-998), multiply and add
+// separate: bit-identical to the reference-order kernel.
+// ------------------------------------------------------------------------------------------
+constexpr int ST_MAXT = 32;
+struct StencilP {
+  int ne, nt, row_axis;
+  unsigned rs[MUL_MAXE], big[MUL_MAXE];     // result extents, extents of the big operand (effective axes)
+  long long bstr[MUL_MAXE];                 // strides of the big operand
+  unsigned char m[ST_MAXT][MUL_MAXE];       // term t pairs small[m_t] with big[k - m_t]
+  unsigned char group_start[ST_MAXT];       // 1: first term of a new outer-axes group
+  unsigned short sidx[ST_MAXT];             // linear index of m_t in the small operand
+  long long delta[ST_MAXT];                 // sum_a m_t[a] * bstr[a]
+  unsigned row_begin, row_step;
+  unsigned total;
+  const double* bigp;
+  const double* smallp;
+  double* out;
+};
+template <int NE>
+__global__ void __launch_bounds__(256) k_mul_stencil(const __grid_constant__ StencilP p) {
+  double sv[ST_MAXT];
+#pragma unroll
+  for (int t = 0; t < ST_MAXT; t++) sv[t] = t < p.nt ? p.smallp[p.sidx[t]] : 0.0;
+  const unsigned gstride = gridDim.x * blockDim.x;
+  for (unsigned lin = blockIdx.x * blockDim.x + threadIdx.x; lin < p.total; lin += gstride) {
+    unsigned k[NE];
+    unsigned rem = lin;
+    long long base = 0;
+#pragma unroll
+    for (int d = NE - 1; d >= 0; --d) {
+      if (d == 0 && p.row_axis) {
+        k[d] = p.row_begin + rem * p.row_step;
+      } else {
+        const unsigned q = rem / p.rs[d];
+        k[d] = rem - q * p.rs[d];
+        rem = q;
+      }
+      base += (long long)k[d] * p.bstr[d];
+    }
+    double total = 0.0, inner = 0.0;
+    bool open = false;    // a group with valid outer axes is being summed
+#pragma unroll
+    for (int t = 0; t < ST_MAXT; t++) {
+      if (t < p.nt) {
+        if (p.group_start[t]) {
+          if (open) total = __dadd_rn(total, inner);
+          inner = 0.0;
+          open = true;
+#pragma unroll
+          for (int d = 0; d < NE - 1; d++) {
+            const unsigned md = p.m[t][d];
+            open = open && k[d] >= md && k[d] - md < p.big[d];
+          }
+        }
+        const unsigned ml = p.m[t][NE - 1];
+        if (open && k[NE - 1] >= ml && k[NE - 1] - ml < p.big[NE - 1])
+          inner = __dadd_rn(inner, __dmul_rn(p.bigp[base - p.delta[t]], sv[t]));
+      }
+    }
+    if (open) total = __dadd_rn(total, inner);
+    p.out[lin] = total;
+  }
+}
+
+// Returns false if the product is not a stencil case (then the caller falls back to the reference-order kernel).
+static bool launch_mul_stencil(Ctx& ctx, const MulArgs& a) {
+  const int nd = a.ndim;
+  if (a.accumulate || !a.rows.empty() || nd == 0 || nd > MAXD) return false;
+  const u64 nx = prod(a.xs), ny = prod(a.ys);
+  const bool small_is_x = nx <= ny;
+  const Shape& ss = small_is_x ? a.xs : a.ys;
+  const Shape& bs = small_is_x ? a.ys : a.xs;
+  const u64 ns = std::min(nx, ny), nb = std::max(nx, ny);
+  if (ns == 0 || ns > (u64)ST_MAXT || nb < 4096) return false;
+  u64 row_elems = 1;
+  for (int i = 1; i < nd; i++) row_elems *= a.rs[i];
+  const u64 row_count = a.rs[0] == 1 ? 1 : a.row_count;
+  const u64 total = row_count * row_elems;
+  if (total == 0 || total >= (1ull << 32) - 65536 || a.row_begin + a.row_count * a.row_step >= (1ull << 32)) return false;
+  for (int d = 0; d < nd; d++)
+    if (ss[d] > 255) return false;
+  StencilP p;
+  memset(&p, 0, sizeof(p));
+  Shape sst(nd, 1), bst(nd, 1);
+  for (int i = nd - 2; i >= 0; --i) {
+    sst[i] = sst[i + 1] * ss[i + 1];
+    bst[i] = bst[i + 1] * bs[i + 1];
+  }
+  std::vector<int> eff;   // effective (non-unit result) axes
+  for (int d = 0; d < nd; d++) {
+    if (a.rs[d] == 1) {
+      if (d == 0 && !(a.row_count <= 1 && a.row_begin == 0)) return false;
+      // operands longer than a unit result axis never come from the operator surface (they are truncated to the
+      // result degrees first); the reference's flattened 1-d leaf gives such shapes a meaning of their own
+      if (a.xs[d] != 1 || a.ys[d] != 1) return false;
+      continue;
+    }
+    eff.push_back(d);
+  }
+  if (eff.empty() || (int)eff.size() > MUL_MAXE) return false;
+  const int ne = (int)eff.size();
+  p.ne = ne;
+  p.row_axis = eff[0] == 0 ? 1 : 0;
+  for (int e = 0; e < ne; e++) {
+    p.rs[e] = (unsigned)a.rs[eff[e]];
+    p.big[e] = (unsigned)bs[eff[e]];
+    p.bstr[e] = (long long)bst[eff[e]];
+  }
+  // the small operand's coefficients that can contribute (index 0 on every unit result axis), in visiting order:
+  // ascending X index <=> ascending m if the small operand is X, descending m if it is Y
+  struct Term { std::vector<unsigned> m; u64 idx; };
+  std::vector<Term> terms;
+  for (u64 lin = 0; lin < ns; lin++) {
+    u64 rem = lin;
+    std::vector<unsigned> full(nd);
+    for (int d = nd - 1; d >= 0; --d) {
+      full[d] = (unsigned)(rem % ss[d]);
+      rem /= ss[d];
+    }
+    bool ok = true;
+    for (int d = 0; d < nd; d++)
+      if (a.rs[d] == 1 && full[d] != 0) ok = false;
+    if (!ok) continue;
+    Term t;
+    t.idx = lin;
+    for (int e = 0; e < ne; e++) t.m.push_back(full[eff[e]]);
+    terms.push_back(t);
+  }
+  if (terms.empty()) return false;
+  std::sort(terms.begin(), terms.end(), [&](const Term& x, const Term& y) { return small_is_x ? x.m < y.m : x.m > y.m; });
+  p.nt = (int)terms.size();
+  for (int t = 0; t < p.nt; t++) {
+    long long delta = 0;
+    for (int e = 0; e < ne; e++) {
+      p.m[t][e] = (unsigned char)terms[t].m[e];
+      delta += (long long)terms[t].m[e] * p.bstr[e];
+    }
+    p.delta[t] = delta;
+    p.sidx[t] = (unsigned short)terms[t].idx;
+    bool new_group = t == 0;
+    for (int e = 0; e < ne - 1 && !new_group; e++) new_group = terms[t].m[e] != terms[t - 1].m[e];
+    p.group_start[t] = new_group ? 1 : 0;
+  }
+  p.row_begin = (unsigned)a.row_begin;
+  p.row_step = (unsigned)a.row_step;
+  p.total = (unsigned)total;
+  p.bigp = small_is_x ? a.y : a.x;
+  p.smallp = small_is_x ? a.x : a.y;
+  p.out = a.out;
+  const int block = 256;
+  const int grid = (int)std::max<u64>(1, std::min<u64>((total + block - 1) / block, (u64)ctx.sm_count * 32));
+  switch (ne) {
+#define CASE(N) case N: GTP_LAUNCH(ctx, k_mul_stencil<N>, grid, block, 0, p); break;
+    CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+#undef CASE
+  }
+  return true;
+}
+
 void launch_mul(Ctx& ctx, const MulArgs& a_in) {
   MulArgs a = a_in;
   if (!a.rows.empty()) {
@@ -205,6 +374,14 @@ void launch_mul(Ctx& ctx, const MulArgs& a_in) {
     a.row_step = 1;
   }
   const int kind = mul_kernel_kind(ctx, a);
+  if (ctx.hist) {   // GTP_LAUNCH_HIST=1: log every product above 10^6 MACs (shape census of real programs)
+    const double macs = args_macs(a);
+    if (macs >= 1e6) {
+      auto sh = [](const Shape& v) { std::string t; for (u64 x : v) t += std::to_string(x) + ","; return t; };
+      fprintf(stderr, "[gtp mul] kind %d macs %.3g x [%s] y [%s] r [%s] rows %llu\n", kind, macs, sh(a.xs).c_str(), sh(a.ys).c_str(),
+              sh(a.rs).c_str(), (unsigned long long)a.row_count);
+    }
+  }
   if (kind == 2) {
     launch_mul_blk(ctx, a);
     return;
@@ -213,6 +390,7 @@ void launch_mul(Ctx& ctx, const MulArgs& a_in) {
     launch_mul_slide(ctx, a);
     return;
   }
+  if (ctx.fast_mul && ctx.use_stencil && launch_mul_stencil(ctx, a)) return;   // bit-exact, HBM-bound small-operand products
   if (a.rows.empty()) {
     launch_mul_ordered(ctx, a);
     return;

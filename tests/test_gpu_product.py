@@ -222,3 +222,30 @@ def test_operator_level_product_uses_fast_kernel(ctx):
     o = O.taylor(x) * O.taylor(y)
     assert g.array_shape() == o.array_shape() and g.shape() == o.shape()
     assert rel_err(g.array(), o.array()) <= RTOL
+
+
+STENCIL = [((40, 30, 40), (2, 1, 2), (41, 30, 41)), ((2, 1, 2), (40, 30, 40), (41, 30, 41)), ((40, 30, 40), (2, 1, 2), (40, 30, 40)),
+           ((64, 80), (3, 2), (66, 81)), ((64, 80), (3, 2), (50, 81)), ((5000,), (7,), (5006,)), ((7,), (5000,), (4000,)),
+           ((20, 20, 20), (1, 3, 1), (20, 22, 20)), ((9, 1, 30, 1, 25), (2, 1, 2, 1, 3), (10, 1, 31, 1, 27)),
+           ((16, 16, 16, 4), (2, 2, 2, 2), (17, 17, 17, 5)), ((300, 40), (1, 32), (300, 71)), ((70, 1, 70), (4, 1, 8), (73, 1, 77))]
+
+
+@pytest.mark.parametrize("xs,ys,rs", STENCIL)
+def test_stencil_product_bit_exact(ctx, xs, ys, rs):
+    """Products with one operand of at most 32 coefficients (multilinear substitutions, thinning factors) take the
+    HBM-bound stencil kernel; it visits the terms in the reference's order, so it is bit-identical to the oracle --
+    either operand small, truncated results, unit axes, signed zeros, and leading-axis row subsets."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(sum(xs) + 7 * sum(ys))
+    x, y = rng.standard_normal(xs), rng.standard_normal(ys)
+    x.flat[rng.integers(0, x.size, max(1, x.size // 11))] = -0.0
+    y.flat[rng.integers(0, y.size, max(1, y.size // 5))] = 0.0
+    ref = O.mul_raw(x, y, rs)
+    got = gpu_mul_raw(ctx, x, y, rs, fast=True)
+    assert np.array_equal(got.view(np.uint64), ref.view(np.uint64))
+    off = gpu_mul_raw(ctx, x, y, rs, fast=257)       # + 256: stencil kernel off -> reference-order kernel
+    assert np.array_equal(off.view(np.uint64), ref.view(np.uint64))
+    if rs[0] > 3:
+        cnt = len(range(1, rs[0], 3))
+        rows = gpu_mul_raw(ctx, x, y, rs, rows=(1, 3, cnt), fast=True)
+        assert np.array_equal(rows.view(np.uint64), ref[1::3].view(np.uint64))
