@@ -14,7 +14,18 @@ BufP Ctx::alloc(u64 n) {
   b->core = core;
   b->owned = true;
   const double t0 = hist ? now() : 0.0;
-  GTP_CUDA(cudaMallocAsync((void**)&b->d, std::max<u64>(n, 1) * sizeof(double), stream));
+  const u64 cls = StreamCore::size_class(std::max<u64>(n, 1) * sizeof(double));
+  b->cls_bytes = cls;
+  b->d = (double*)core->take(cls);
+  if (!b->d) {
+    cudaError_t e = cudaMallocAsync((void**)&b->d, cls, stream);
+    if (e == cudaErrorMemoryAllocation) {   // give the cached blocks back and try once more
+      cudaGetLastError();
+      core->trim();
+      e = cudaMallocAsync((void**)&b->d, cls, stream);
+    }
+    GTP_CUDA(e);
+  }
   if (hist) t_alloc += now() - t0;
   if (!fused_cls.empty()) fused_cls.erase(b->d);   // a classification recorded for an earlier tensor at this address is stale
   return b;
@@ -129,28 +140,23 @@ static bool classify_from_producer(Ctx& c, const gtp_poly& p) {
   if (c.cls_seq - seq >= Ctx::CLS_RING) return false;   // the ring has wrapped past this slot
   const ClsSlot* slot = c.cls_ring + (seq % Ctx::CLS_RING);
   const double t0 = c.hist ? Ctx::now() : 0.0;
-  for (unsigned long long spins = 0; slot->seq != seq; ++spins) {
-    if (slot->seq > seq) return false;
+  auto ready = [&] { return slot->seq_a == seq && slot->seq_b == (unsigned)seq; };
+  for (unsigned long long spins = 0; !ready(); ++spins) {
+    if (slot->seq_a > seq) return false;
     if ((spins & 0xfffff) == 0xfffff) {
       cudaError_t e = cudaStreamQuery(c.stream);
       if (e != cudaSuccess && e != cudaErrorNotReady) GTP_CUDA(e);
-      if (e == cudaSuccess && slot->seq != seq) return false;
+      if (e == cudaSuccess && !ready()) return false;
     }
   }
   if (c.hist) c.t_spin += Ctx::now() - t0;
   std::atomic_thread_fence(std::memory_order_acquire);
   p.cls->first = slot->first;
-  p.cls->linear = false;
-  const unsigned viol = slot->viol_mask;
-  for (size_t v = 0; v < p.shape.size(); v++) {
-    if (p.shape[v] < 2) continue;
-    if (!(viol & (1u << v))) {
-      p.cls->linear = true;
-      p.cls->c = p.cls->first;
-      p.cls->m = slot->slope[v];
-      p.cls->v = v;
-      break;
-    }
+  p.cls->linear = slot->axis_p1 != 0;      // 1 + the first stored axis of length >= 2 that qualifies (:277-292)
+  if (p.cls->linear) {
+    p.cls->c = p.cls->first;
+    p.cls->m = slot->m;
+    p.cls->v = slot->axis_p1 - 1;
   }
   p.cls->known = true;
   c.fused_hits++;

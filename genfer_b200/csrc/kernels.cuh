@@ -73,14 +73,20 @@ __device__ __forceinline__ void cls_epilogue(const double* in, const ClsParams& 
   }
   if (mask) atomicOr(&cls_sh_mask, mask);
   __syncthreads();
-  if ((int)threadIdx.x < p.ndim) slot->slope[threadIdx.x] = p.shape[threadIdx.x] >= 2 ? in[p.str[threadIdx.x]] : 0.0;
+  // ONE thread talks to host memory: payload, one system-scope fence, then the sequence number (with every thread
+  // fencing and ndim threads storing slopes the epilogue cost 5.7 us per launch)
   if (threadIdx.x == 0) {
-    slot->first = in[0];
-    slot->viol_mask = cls_sh_mask;
+    const unsigned viol = cls_sh_mask;
+    int v = -1;
+    for (int d = 0; d < p.ndim; d++)
+      if (p.shape[d] >= 2 && !(viol & (1u << d))) { v = d; break; }
+    // No fence: each 16-byte half of the slot travels as one store (one PCIe write) together with its copy of the
+    // sequence number, and the host waits for both copies -- a system-scope fence between payload and flag cost 3.8 us.
+    const double first = in[0], m = v >= 0 ? in[p.str[v]] : 0.0;
+    const unsigned long long tag_b = ((unsigned long long)(unsigned)seq << 32) | (unsigned)(v + 1);   // {axis_p1, seq_b}
+    asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(&slot->first), "l"(__double_as_longlong(first)), "l"(seq) : "memory");
+    asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(&slot->m), "l"(__double_as_longlong(m)), "l"(tag_b) : "memory");
   }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) slot->seq = seq;
 }
 struct FusedClsArgs {   // kernel-side half of a fused classification (slot == nullptr: none)
   ClsSlot* slot;

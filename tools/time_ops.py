@@ -88,6 +88,21 @@ emit(op="add                    [a6]", shape=args.shape, ms=round(ms, 4), algori
      frac_of_hbm=round(gbs / HBM, 3), hbm_peak=HBM, launches_per_call=launches)
 del T, xs
 
+# ---- stencil product (a7 with a small operand): the heavy product of the population models --------------------------
+for xs_, ys_ in (((297, 282, 297), (2, 1, 2)), ((16,) * 6, (2, 1, 2, 1, 1, 2))):
+    rs_ = tuple(a + b - 1 for a, b in zip(xs_, ys_))
+    bigs = [torch.rand(xs_, dtype=torch.float64, device="cuda") for _ in range(3)]
+    small = torch.rand(ys_, dtype=torch.float64, device="cuda")
+    Tb = [TP.from_device(b.data_ptr(), xs_, rs_, ctx) for b in bigs]
+    Ts = TP.from_device(small.data_ptr(), ys_, rs_, ctx)
+    ms, launches = timed([lambda t=t: t * Ts for t in Tb])
+    nx, nz = int(np.prod(xs_)), int(np.prod(rs_))
+    gbs = 8.0 * (nx + nz) / (ms * 1e-3) / 1e9
+    emit(op="mul by a small operand (stencil kernel) [a7]", shape=f"{list(xs_)} x {list(ys_)}", ms=round(ms, 4),
+         algorithmic_bytes=8 * (nx + nz), gbs=round(gbs, 1), frac_of_hbm=round(gbs / HBM, 3), hbm_peak=HBM,
+         macs=genfer_b200.mul_macs(xs_, ys_, rs_), launches_per_call=launches)
+    del Tb, Ts, bigs, small
+
 # ---- recurrences ----------------------------------------------------------------------------------------
 peak_fl, _ = ctx.fp64_peak_probe(0, 16384)
 for cfg in args.rec_shape.split(","):
