@@ -225,11 +225,13 @@ struct StencilP {
   const double* smallp;
   double* out;
 };
-template <int NE>
+// NT: compile-time bound on the number of terms (2, 4, 8, 16, 32): with a single 32-term body ptxas predicates all 32
+// term bodies and a 4-term product executes ~700 instructions per coefficient.
+template <int NE, int NT>
 __global__ void __launch_bounds__(256) k_mul_stencil(const __grid_constant__ StencilP p) {
-  double sv[ST_MAXT];
+  double sv[NT];
 #pragma unroll
-  for (int t = 0; t < ST_MAXT; t++) sv[t] = t < p.nt ? p.smallp[p.sidx[t]] : 0.0;
+  for (int t = 0; t < NT; t++) sv[t] = t < p.nt ? p.smallp[p.sidx[t]] : 0.0;
   const unsigned gstride = gridDim.x * blockDim.x;
   for (unsigned lin = blockIdx.x * blockDim.x + threadIdx.x; lin < p.total; lin += gstride) {
     unsigned k[NE];
@@ -249,7 +251,7 @@ __global__ void __launch_bounds__(256) k_mul_stencil(const __grid_constant__ Ste
     double total = 0.0, inner = 0.0;
     bool open = false;    // a group with valid outer axes is being summed
 #pragma unroll
-    for (int t = 0; t < ST_MAXT; t++) {
+    for (int t = 0; t < NT; t++) {
       if (t < p.nt) {
         if (p.group_start[t]) {
           if (open) total = __dadd_rn(total, inner);
@@ -358,11 +360,14 @@ static bool launch_mul_stencil(Ctx& ctx, const MulArgs& a) {
   p.out = a.out;
   const int block = 256;
   const int grid = (int)std::max<u64>(1, std::min<u64>((total + block - 1) / block, (u64)ctx.sm_count * 32));
+  const int bucket = p.nt <= 2 ? 2 : p.nt <= 4 ? 4 : p.nt <= 8 ? 8 : p.nt <= 16 ? 16 : 32;
+#define CASE_NT(N, T) case T: GTP_LAUNCH(ctx, (k_mul_stencil<N, T>), grid, block, 0, p); break;
+#define CASE(N) case N: switch (bucket) { CASE_NT(N, 2) CASE_NT(N, 4) CASE_NT(N, 8) CASE_NT(N, 16) CASE_NT(N, 32) } break;
   switch (ne) {
-#define CASE(N) case N: GTP_LAUNCH(ctx, k_mul_stencil<N>, grid, block, 0, p); break;
     CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
-#undef CASE
   }
+#undef CASE
+#undef CASE_NT
   return true;
 }
 
