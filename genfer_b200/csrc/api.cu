@@ -894,6 +894,7 @@ int gtp_ctx_set_fast_mul(gtp_ctx* c, int enabled) {
   c->use_slide = (enabled & 16) == 0;
   c->fuse_mul_linear = (enabled & 128) == 0;
   c->use_stencil = (enabled & 256) == 0;
+  c->stencil_v4 = (enabled & 512) == 0;
   c->slide_tile = ((enabled >> 5) & 3) == 1 ? 4 : (((enabled >> 5) & 3) == 2 ? 8 : 0);   // A/B measurements
   enabled &= 3;
   c->fast_mul = enabled < 0 ? 0 : (enabled > 2 ? 2 : enabled);

@@ -202,6 +202,7 @@ struct Ctx {
   std::shared_ptr<void> slide_plans; // same for kernels_mul_slide.cu
   bool use_slide = true;             // sliding 1x2 kernel for dense cube slabs (false: 2x2-blocked kernel everywhere)
   int slide_tile = 0;                // 0: auto; 4 / 8: force the plane-tiled sliding plan with that many planes per slab
+  bool stencil_v4 = true;            // stencil kernel: four coefficients per thread (false: one; A/B tests, bit 512)
   bool use_stencil = true;           // small-operand stencil product kernel (false: reference-order kernel; A/B tests)
   bool fuse_mul_linear = true;       // one-pass mul_linear kernel (false: the reference's composition, for A/B tests)
   bool blk_octet = false;            // experimental octet tables for single-plane slabs (8 staged pairs = 8 lanes)

@@ -220,7 +220,8 @@ struct StencilP {
   unsigned short sidx[ST_MAXT];             // linear index of m_t in the small operand
   long long delta[ST_MAXT];                 // sum_a m_t[a] * bstr[a]
   unsigned row_begin, row_step;
-  unsigned total;
+  unsigned total;                           // coefficients (k_mul_stencil) or units of four (k_mul_stencil_v4)
+  unsigned lastq;                           // v4: units per row of the innermost effective axis
   const double* bigp;
   const double* smallp;
   double* out;
@@ -270,6 +271,71 @@ __global__ void __launch_bounds__(256) k_mul_stencil(const __grid_constant__ Ste
     }
     if (open) total = __dadd_rn(total, inner);
     p.out[lin] = total;
+  }
+}
+
+// Four consecutive coefficients of the innermost effective axis per thread: the index decode, the outer-axis validity
+// tests and the group bookkeeping are shared by the four, which halves the instructions per coefficient again.  The
+// per-coefficient order of operations is unchanged.  (The big operand's innermost effective stride is 1: unit result axes
+// have unit operands, see launch_mul_stencil.)  p.total counts units of four; p.lastq = ceil(rs_last / 4).
+template <int NE, int NT>
+__global__ void __launch_bounds__(256) k_mul_stencil_v4(const __grid_constant__ StencilP p) {
+  static_assert(NE >= 2, "the innermost effective axis must not be the row axis");
+  double sv[NT];
+#pragma unroll
+  for (int t = 0; t < NT; t++) sv[t] = t < p.nt ? p.smallp[p.sidx[t]] : 0.0;
+  const unsigned gstride = gridDim.x * blockDim.x;
+  const unsigned rl = p.rs[NE - 1], bl = p.big[NE - 1];
+  for (unsigned unit = blockIdx.x * blockDim.x + threadIdx.x; unit < p.total; unit += gstride) {
+    unsigned k[NE];
+    unsigned rem = unit / p.lastq;
+    const unsigned kl0 = (unit - rem * p.lastq) * 4u;
+    const unsigned outer_lin = rem;
+    long long base = (long long)kl0;
+#pragma unroll
+    for (int d = NE - 2; d >= 0; --d) {
+      if (d == 0 && p.row_axis) {
+        k[d] = p.row_begin + rem * p.row_step;
+      } else {
+        const unsigned q = rem / p.rs[d];
+        k[d] = rem - q * p.rs[d];
+        rem = q;
+      }
+      base += (long long)k[d] * p.bstr[d];
+    }
+    double total[4] = {0.0, 0.0, 0.0, 0.0}, inner[4] = {0.0, 0.0, 0.0, 0.0};
+    bool open = false;
+#pragma unroll
+    for (int t = 0; t < NT; t++) {
+      if (t < p.nt) {
+        if (p.group_start[t]) {
+          if (open) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) total[i] = __dadd_rn(total[i], inner[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; i++) inner[i] = 0.0;
+          open = true;
+#pragma unroll
+          for (int d = 0; d < NE - 1; d++) open = open && (k[d] - (unsigned)p.m[t][d]) < p.big[d];   // unsigned: k >= m too
+        }
+        if (open) {
+          const unsigned ml = p.m[t][NE - 1];
+          const double* src = p.bigp + (base - p.delta[t]);
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const unsigned kk = kl0 + i;
+            if (kk < rl && (kk - ml) < bl) inner[i] = __dadd_rn(inner[i], __dmul_rn(src[i], sv[t]));
+          }
+        }
+      }
+    }
+    double* dst = p.out + (size_t)outer_lin * rl + kl0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (open) total[i] = __dadd_rn(total[i], inner[i]);
+      if (kl0 + i < rl) dst[i] = total[i];
+    }
   }
 }
 
@@ -361,6 +427,20 @@ static bool launch_mul_stencil(Ctx& ctx, const MulArgs& a) {
   const int block = 256;
   const int grid = (int)std::max<u64>(1, std::min<u64>((total + block - 1) / block, (u64)ctx.sm_count * 32));
   const int bucket = p.nt <= 2 ? 2 : p.nt <= 4 ? 4 : p.nt <= 8 ? 8 : p.nt <= 16 ? 16 : 32;
+  if (ne >= 2 && p.rs[ne - 1] >= 8 && p.bstr[ne - 1] == 1 && ctx.stencil_v4) {
+    p.lastq = (p.rs[ne - 1] + 3) / 4;
+    const u64 units = (total / p.rs[ne - 1]) * p.lastq;
+    p.total = (unsigned)units;
+    const int gridv = (int)std::max<u64>(1, std::min<u64>((units + block - 1) / block, (u64)ctx.sm_count * 32));
+#define CASE_NT(N, T) case T: GTP_LAUNCH(ctx, (k_mul_stencil_v4<N, T>), gridv, block, 0, p); break;
+#define CASE(N) case N: switch (bucket) { CASE_NT(N, 2) CASE_NT(N, 4) CASE_NT(N, 8) CASE_NT(N, 16) CASE_NT(N, 32) } break;
+    switch (ne) {
+      CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+    }
+#undef CASE
+#undef CASE_NT
+    return true;
+  }
 #define CASE_NT(N, T) case T: GTP_LAUNCH(ctx, (k_mul_stencil<N, T>), grid, block, 0, p); break;
 #define CASE(N) case N: switch (bucket) { CASE_NT(N, 2) CASE_NT(N, 4) CASE_NT(N, 8) CASE_NT(N, 16) CASE_NT(N, 32) } break;
   switch (ne) {

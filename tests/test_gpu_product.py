@@ -245,6 +245,8 @@ def test_stencil_product_bit_exact(ctx, xs, ys, rs):
     assert np.array_equal(got.view(np.uint64), ref.view(np.uint64))
     off = gpu_mul_raw(ctx, x, y, rs, fast=257)       # + 256: stencil kernel off -> reference-order kernel
     assert np.array_equal(off.view(np.uint64), ref.view(np.uint64))
+    one = gpu_mul_raw(ctx, x, y, rs, fast=513)       # + 512: one coefficient per thread instead of four
+    assert np.array_equal(one.view(np.uint64), ref.view(np.uint64))
     if rs[0] > 3:
         cnt = len(range(1, rs[0], 3))
         rows = gpu_mul_raw(ctx, x, y, rs, rows=(1, 3, cnt), fast=True)
