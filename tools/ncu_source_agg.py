@@ -9,7 +9,7 @@ rows = list(csv.reader(txt.splitlines()))
 hdr = rows[1]
 H = {h: i for i, h in enumerate(hdr)}
 body = rows[2:]
-f = lambda r, k: float(r[H[k]] or 0)
+f = lambda r, k: float(r[H[k]] or 0) if k in H else 0.0
 tot_samples = sum(f(r, "# Samples") for r in body)
 agg = {}
 stall_cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
