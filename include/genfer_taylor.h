@@ -83,6 +83,8 @@ int gtp_from_host(gtp_ctx* ctx, int ndim, const uint64_t* shape, const uint64_t*
 int gtp_from_device(gtp_ctx* ctx, int ndim, const uint64_t* shape, const uint64_t* degrees_p1,
                     const double* device_data, gtp_poly** out);
 int gtp_to_host(gtp_ctx* ctx, const gtp_poly* p, double* out); /* into_array (:63-66); synchronises */
+/* address of the stored coefficients, valid in kernels on the context's stream.  For tensors of one or two coefficients
+ * created by gtp_from_scalar / gtp_var* it is a mapped pinned HOST address (unified addressing), otherwise device memory. */
 int gtp_device_ptr(gtp_ctx* ctx, const gtp_poly* p, const double** out);
 int gtp_clone(gtp_ctx* ctx, const gtp_poly* p, gtp_poly** out); /* Clone (:10) */
 void gtp_free(gtp_ctx* ctx, gtp_poly* p);
