@@ -23,6 +23,8 @@ struct GpuBackend {
     Handle& operator=(const Handle&) = delete;
   };
   using Poly = std::shared_ptr<Handle>;
+  using Scalar = double;   // the f64 Number path (the only one on the device)
+  static double scalar_max(double x, double y) { return x > y ? x : y; }   // F64::max (number/f64.rs:77-84)
 
   void check(int rc) const {
     if (rc != 0) throw gfe::EvalError(std::string("libgenfer_taylor: ") + gtp_last_error(ctx));

@@ -23,6 +23,9 @@ template <class B>
 class Evaluator {
  public:
   using Poly = typename B::Poly;
+  // The scalar type T of the reference's TaylorPoly<T>: double in the product (GpuBackend) and in the f64 oracle; the
+  // oracle's --bounds instantiation uses Interval<F64>.  GenFun constants stay f64 (they become point intervals).
+  using S = typename B::Scalar;
   explicit Evaluator(B& backend) : b_(backend) {}
 
   // ---- simplify (:152-177, :474-545) ---------------------------------------------------------------
@@ -37,53 +40,53 @@ class Evaluator {
   }
 
   // ---- eval (:179-222) -----------------------------------------------------------------------------------
-  Poly eval(const GenFun& g, const std::vector<double>& inputs, size_t degree_p1) {
+  Poly eval(const GenFun& g, const std::vector<S>& inputs, size_t degree_p1) {
     eval_cache_.clear();
     return eval_with(g, inputs, degree_p1);
   }
 
   // probs_taylor (:937-967): p(0..max_n) of variable v
-  std::vector<double> probs_taylor(const GenFun& pgf, Var v, const VarSupport& vi, size_t max_n) {
+  std::vector<S> probs_taylor(const GenFun& pgf, Var v, const VarSupport& vi, size_t max_n) {
     GFE_ASSERT(vi[v].is_discrete(), "Can only compute probabilities for discrete variables");
-    std::vector<double> substs(vi.num_vars());
-    for (size_t i = 0; i < substs.size(); i++) substs[i] = vi[i].is_discrete() ? 1.0 : 0.0;
-    substs[v] = 0.0;
+    std::vector<S> substs(vi.num_vars(), S(0.0));
+    for (size_t i = 0; i < substs.size(); i++) substs[i] = vi[i].is_discrete() ? S(1.0) : S(0.0);
+    substs[v] = S(0.0);
     Poly expansion = eval(pgf, substs, max_n + 1);
     return b_.gather_axis(expansion, v, max_n);   // `max_n` coefficient() reads as ONE gather
   }
 
   // moments_taylor (:970-1005): (total, raw moments of order 1..limit-1)
-  std::pair<double, std::vector<double>> moments_taylor(const GenFun& pgf, Var v, const VarSupport& vi, size_t limit) {
-    std::vector<double> substs(vi.num_vars());
-    for (size_t i = 0; i < substs.size(); i++) substs[i] = vi[i].is_discrete() ? 1.0 : 0.0;
+  std::pair<S, std::vector<S>> moments_taylor(const GenFun& pgf, Var v, const VarSupport& vi, size_t limit) {
+    std::vector<S> substs(vi.num_vars(), S(0.0));
+    for (size_t i = 0; i < substs.size(); i++) substs[i] = vi[i].is_discrete() ? S(1.0) : S(0.0);
     Poly expansion = eval(pgf, substs, limit);
-    std::vector<double> coeffs = b_.gather_axis(expansion, v, limit);
-    std::vector<double> result;
-    double factor = 1.0;
+    std::vector<S> coeffs = b_.gather_axis(expansion, v, limit);
+    std::vector<S> result;
+    S factor = S(1.0);
     for (size_t i = 0; i < limit; i++) {
       result.push_back(coeffs[i] * factor);
-      factor *= (double)(uint32_t)(i + 1);
+      factor = factor * S((double)(uint32_t)(i + 1));
     }
     if (vi[v].is_discrete()) return factorial_moments_to_moments(result);
-    double total = result[0];
-    std::vector<double> moments;
+    S total = result[0];
+    std::vector<S> moments;
     for (size_t i = 1; i < result.size(); i++) moments.push_back(result[i] / total);
     return {total, moments};
   }
 
-  static std::pair<double, std::vector<double>> factorial_moments_to_moments(const std::vector<double>& fm) {  // :1008-1033
+  static std::pair<S, std::vector<S>> factorial_moments_to_moments(const std::vector<S>& fm) {  // :1008-1033
     const size_t len = fm.size();
-    std::vector<std::vector<double>> st(len, std::vector<double>(len, 0.0));
+    std::vector<std::vector<S>> st(len, std::vector<S>(len, S(0.0)));
     for (size_t n = 0; n < len; n++) {
-      st[n][0] = 0.0;
-      st[n][n] = 1.0;
-      for (size_t k = 1; k < n; k++) st[n][k] = st[n - 1][k - 1] + (double)(uint32_t)k * st[n - 1][k];
+      st[n][0] = S(0.0);
+      st[n][n] = S(1.0);
+      for (size_t k = 1; k < n; k++) st[n][k] = st[n - 1][k - 1] + S((double)(uint32_t)k) * st[n - 1][k];
     }
-    double total = fm[0];
-    std::vector<double> moments(len - 1, 0.0);
+    S total = fm[0];
+    std::vector<S> moments(len - 1, S(0.0));
     for (size_t n = 1; n < len; n++)
-      for (size_t k = 0; k <= n; k++) moments[n - 1] += st[n][k] * fm[k];
-    for (double& m : moments) m /= total;
+      for (size_t k = 0; k <= n; k++) moments[n - 1] = moments[n - 1] + st[n][k] * fm[k];
+    for (S& m : moments) m = m / total;
     return {total, moments};
   }
 
@@ -94,10 +97,10 @@ class Evaluator {
   std::unordered_map<const GfNode*, std::pair<GenFun, std::optional<Poly>>> simp_cache_;
   // the entry keeps its node alive (like EvalResult.gf in the reference): temporaries built during evaluation are
   // freed again, and a later node allocated at the same address must not hit a stale entry
-  struct EvalEntry { GenFun node; std::vector<double> inputs; size_t degree_p1; Poly output; };
+  struct EvalEntry { GenFun node; std::vector<S> inputs; size_t degree_p1; Poly output; };
   std::unordered_map<const GfNode*, EvalEntry> eval_cache_;
 
-  static bool same_inputs(const std::vector<double>& a, const std::vector<double>& b) {
+  static bool same_inputs(const std::vector<S>& a, const std::vector<S>& b) {
     if (a.size() != b.size()) return false;
     for (size_t i = 0; i < a.size(); i++)
       if (!(a[i] == b[i])) return false;   // PartialEq on f64
@@ -117,8 +120,8 @@ class Evaluator {
 
   std::optional<Poly> simplify_node(const GfNode& n) {
     switch (n.kind) {
-      case GfNode::Var: return b_.var_with_degrees(n.var, 0.0, std::vector<uint64_t>(n.var + 1, UNBOUNDED));
-      case GfNode::Const: return b_.from_scalar(n.value);
+      case GfNode::Var: return b_.var_with_degrees(n.var, S(0.0), std::vector<uint64_t>(n.var + 1, UNBOUNDED));
+      case GfNode::Const: return b_.from_scalar(S(n.value));
       case GfNode::Add: case GfNode::Mul: case GfNode::Div: {
         auto p1 = simplify_with(n.a);
         auto p2 = simplify_with(n.b);
@@ -157,7 +160,7 @@ class Evaluator {
     return std::nullopt;
   }
 
-  Poly eval_with(const GenFun& g, const std::vector<double>& inputs, size_t degree_p1) {
+  Poly eval_with(const GenFun& g, const std::vector<S>& inputs, size_t degree_p1) {
     const bool shared = g.use_count() > 1;
     if (shared) {
       auto it = eval_cache_.find(g.get());
@@ -172,11 +175,11 @@ class Evaluator {
     return r;
   }
 
-  Poly eval_node(const GenFun& g, const std::vector<double>& inputs, size_t degree_p1) {
+  Poly eval_node(const GenFun& g, const std::vector<S>& inputs, size_t degree_p1) {
     const GfNode& n = *g;
     switch (n.kind) {
       case GfNode::Var: return b_.var(n.var, inputs.at(n.var), degree_p1);
-      case GfNode::Const: return b_.from_scalar(n.value);
+      case GfNode::Const: return b_.from_scalar(S(n.value));
       case GfNode::Add: { Poly x = eval_with(n.a, inputs, degree_p1); Poly y = eval_with(n.b, inputs, degree_p1); return b_.add(x, y); }
       case GfNode::Neg: return b_.neg(eval_with(n.a, inputs, degree_p1));
       case GfNode::Mul: { Poly x = eval_with(n.a, inputs, degree_p1); Poly y = eval_with(n.b, inputs, degree_p1); return b_.mul(x, y); }
@@ -197,16 +200,16 @@ class Evaluator {
       case GfNode::Max: {
         Poly s = eval_with(n.a, inputs, degree_p1);
         Poly t = eval_with(n.b, inputs, degree_p1);
-        double x = b_.constant_term(s), y = b_.constant_term(t);
-        return b_.from_scalar(x > y ? x : y);   // F64::max (number/f64.rs:77-84)
+        S x = b_.constant_term(s), y = b_.constant_term(t);
+        return b_.from_scalar(B::scalar_max(x, y));   // F64::max (number/f64.rs:77-84)
       }
       case GfNode::Pow: return b_.pow(eval_with(n.a, inputs, degree_p1), n.n);
       case GfNode::UniformMgf: {  // (e^x - 1) / x, :597-610
         Poly x = eval_with(n.a, inputs, degree_p1);
-        if (b_.constant_term(x) == 0.0) {
+        if (b_.constant_term(x) == S(0.0)) {
           Poly y = b_.var_at_zero(0, degree_p1 + 1);
-          Poly numerator = b_.sub(b_.exp(y), b_.from_scalar(1.0));
-          std::vector<double> arr = b_.to_host(numerator);          // 1-D, length degree_p1 + 1
+          Poly numerator = b_.sub(b_.exp(y), b_.from_scalar(S(1.0)));
+          std::vector<S> arr = b_.to_host(numerator);          // 1-D, length degree_p1 + 1
           std::vector<uint64_t> shape = b_.array_shape(numerator);
           GFE_ASSERT(shape.size() == 1 && shape[0] >= 1, "unexpected shape in UniformMgf");
           std::vector<uint64_t> nshape{shape[0] - 1};
@@ -214,13 +217,13 @@ class Evaluator {
           Poly fraction = b_.new_poly(nshape, std::vector<uint64_t>{(uint64_t)degree_p1}, arr.data() + 1);   // divide by y
           return b_.subst_var(fraction, 0, x);
         }
-        Poly numerator = b_.sub(b_.exp(x), b_.from_scalar(1.0));
+        Poly numerator = b_.sub(b_.exp(x), b_.from_scalar(S(1.0)));
         return b_.truncate_to_degree_p1(b_.div(numerator, x), degree_p1);
       }
       case GfNode::Subst: {  // :611-629
-        std::vector<double> new_inputs = inputs;
+        std::vector<S> new_inputs = inputs;
         Poly subst = eval_with(n.b, inputs, degree_p1);
-        double c = b_.constant_term(subst);
+        S c = b_.constant_term(subst);
         subst = b_.sub(subst, b_.from_scalar(c));
         if (n.var < inputs.size()) new_inputs[n.var] = c;
         else {
@@ -240,8 +243,8 @@ class Evaluator {
         return b_.truncate_to_degree_p1(b_.derivative(t, n.var, n.order), degree_p1);
       }
       case GfNode::TaylorPolynomial: {
-        std::vector<double> new_inputs = inputs;
-        new_inputs.at(n.var) = 0.0;
+        std::vector<S> new_inputs = inputs;
+        new_inputs.at(n.var) = S(0.0);
         size_t max_order = 0;
         for (size_t o : n.orders) max_order = std::max(max_order, o);
         Poly t = eval_with(n.a, new_inputs, degree_p1 + max_order);
@@ -255,7 +258,7 @@ class Evaluator {
         return b_.truncate_to_degree_p1(b_.taylor_expansion_of_coeff(t, n.var, n.order), degree_p1);
       }
       case GfNode::ShiftTaylorAtZero: {
-        if (inputs.at(n.var) == 0.0) {
+        if (inputs.at(n.var) == S(0.0)) {
           Poly t = eval_with(n.a, inputs, degree_p1 + n.order);
           return b_.truncate_to_degree_p1(b_.shift_down(t, n.var, n.order), degree_p1);
         }
@@ -270,7 +273,7 @@ class Evaluator {
     throw EvalError("unreachable");
   }
 
-  Poly eval_taylor_coeff_at_zero(const GenFun& g, Var v, size_t order, const std::vector<double>& inputs, size_t degree_p1) {  // :670-765
+  Poly eval_taylor_coeff_at_zero(const GenFun& g, Var v, size_t order, const std::vector<S>& inputs, size_t degree_p1) {  // :670-765
     gf::Recognised rec;
     if (gf::recognize_discrete_poisson_observation(g, v, &rec)) {
       // D^n(G) with D(G)(y) := lambda y G'(y), evaluated at y = e^(-lambda) y; the 1/n! is folded into the loop
@@ -303,29 +306,29 @@ class Evaluator {
         lahs = next;
       }
       Poly sum = b_.zero_with(std::vector<uint64_t>(inputs.size(), degree_p1));
-      std::vector<double> new_inputs = inputs;
-      new_inputs.at(rec.param_var) = p * inputs[rec.param_var];
+      std::vector<S> new_inputs = inputs;
+      new_inputs.at(rec.param_var) = S(p) * inputs[rec.param_var];
       Poly inner_result = eval_with(rec.inner, new_inputs, degree_p1 + order);
-      Poly power = b_.from_scalar(1.0);
+      Poly power = b_.from_scalar(S(1.0));
       Poly param_tp = b_.var(rec.param_var, inputs[rec.param_var], degree_p1);
-      Poly p_param = b_.mul(b_.from_scalar(p), param_tp);
+      Poly p_param = b_.mul(b_.from_scalar(S(p)), param_tp);
       for (double lah : lahs) {
-        Poly subst = b_.mul(b_.from_scalar(p), b_.var_at_zero(rec.param_var, degree_p1));
-        Poly term = b_.mul(b_.mul(b_.subst_var(inner_result, rec.param_var, subst), power), b_.from_scalar(lah));
+        Poly subst = b_.mul(b_.from_scalar(S(p)), b_.var_at_zero(rec.param_var, degree_p1));
+        Poly term = b_.mul(b_.mul(b_.subst_var(inner_result, rec.param_var, subst), power), b_.from_scalar(S(lah)));
         sum = b_.add(sum, term);
         power = b_.mul(power, p_param);
         inner_result = b_.derivative(inner_result, rec.param_var, 1);
       }
       return b_.truncate_to_degree_p1(sum, degree_p1);
     }
-    std::vector<double> in = inputs;
+    std::vector<S> in = inputs;
     Poly result;
     if (v == in.size()) {
-      in.push_back(0.0);
+      in.push_back(S(0.0));
       Poly t = eval_with(g, in, degree_p1 + order);
       result = b_.remove_last_variable(b_.coefficients_of_term(t, v, order));
     } else {
-      in.at(v) = 0.0;
+      in.at(v) = S(0.0);
       Poly t = eval_with(g, in, degree_p1 + order);
       result = b_.coefficients_of_term(t, v, order);
     }

@@ -468,5 +468,32 @@ def run_sgcl(source: str, limit: Optional[int] = None, no_probs: bool = False, n
         L.orc_sgcl_free(h)
 
 
+class SgclBounds:
+    """Enclosures [lo, hi] of the evaluator's direct outputs (oracle_eval.cpp::orc_run_sgcl_bounds)."""
+
+    def __init__(self, rest, total, raw_moments, probs):
+        self.rest = rest                  # mass of the `rest` generating function
+        self.total = total                # Z before the rest mass is added and before clamping to [0, 1]
+        self.raw_moments = raw_moments    # E[X], E[X^2], E[X^3], E[X^4] (normalised by Z)
+        self.probs = probs                # unnormalised p(0..limit-1)
+
+
+def run_sgcl_bounds(source: str, limit: int = 0, unroll: int = 8) -> SgclBounds:
+    """The host evaluator instantiated over TaylorPoly<Interval<F64>> (the arithmetic of the reference's --bounds mode,
+    src/interval.rs) on the DAG the f64 path evaluates: GenFun constants are the f64 values, as point intervals; no
+    simplification pass.  PARITY UNPINNED: no reference fixture runs with --bounds."""
+    L = lib()
+    L.orc_run_sgcl_bounds.argtypes = [C.c_char_p, C.c_int64, C.c_uint64, _f64p, _f64p, C.c_char_p, C.c_size_t]
+    out = (C.c_double * 12)()
+    probs = (C.c_double * max(2 * limit, 2))()
+    err = C.create_string_buffer(2048)
+    rc = L.orc_run_sgcl_bounds(source.encode(), int(limit), unroll, out, probs, err, 2048)
+    if rc != 0:
+        raise OracleError(err.value.decode())
+    o = list(out)
+    return SgclBounds((o[0], o[1]), (o[2], o[3]), [(o[4 + 2 * i], o[5 + 2 * i]) for i in range(4)],
+                      [(probs[2 * i], probs[2 * i + 1]) for i in range(limit)])
+
+
 def mul_macs(xshape, yshape, rshape) -> float:
     return lib().orc_mul_macs(len(rshape), _u64(xshape), _u64(yshape), _u64(rshape))

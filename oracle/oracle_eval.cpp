@@ -12,24 +12,63 @@
 
 namespace {
 
-using TP = orc::TaylorPoly<double>;
+// Scalar adaptors: how the evaluator's scalar type S maps onto the element type T of the oracle's TaylorPoly<T>.
+struct F64Scalar {
+  using T = double;
+  using S = double;
+  static T raw(S x) { return x; }
+  static S wrap(T x) { return x; }
+  static S max(S x, S y) { return x > y ? x : y; }   // F64::max (number/f64.rs:77-84)
+};
+// Interval<F64> (src/interval.rs) as the evaluator sees it: constructible from an f64 constant (a point interval)
+struct IvS {
+  orc::Interval v{0.0, 0.0};
+  IvS() = default;
+  IvS(double x) : v{x, x} {}
+  explicit IvS(orc::Interval i) : v(i) {}
+  friend IvS operator+(const IvS& a, const IvS& b) { return IvS(a.v + b.v); }
+  friend IvS operator-(const IvS& a, const IvS& b) { return IvS(a.v - b.v); }
+  friend IvS operator*(const IvS& a, const IvS& b) { return IvS(a.v * b.v); }
+  friend IvS operator/(const IvS& a, const IvS& b) { return IvS(a.v / b.v); }
+  friend bool operator==(const IvS& a, const IvS& b) { return a.v == b.v; }
+};
+struct IvScalar {
+  using T = orc::Interval;
+  using S = IvS;
+  static T raw(const S& x) { return x.v; }
+  static S wrap(const T& x) { return IvS(x); }
+  static S max(const S& x, const S& y) {   // Interval::max (interval.rs): componentwise
+    return IvS(orc::Interval{x.v.lo > y.v.lo ? x.v.lo : y.v.lo, x.v.hi > y.v.hi ? x.v.hi : y.v.hi});
+  }
+};
 
-struct OracleBackend {
+template <class A>
+struct OracleBackendT {
+  using T = typename A::T;
+  using Scalar = typename A::S;
+  using TP = orc::TaylorPoly<T>;
   using Poly = std::shared_ptr<const TP>;
+  static Scalar scalar_max(const Scalar& x, const Scalar& y) { return A::max(x, y); }
   static Poly mk(TP t) { return std::make_shared<const TP>(std::move(t)); }
   static std::vector<orc::usize> us(const std::vector<uint64_t>& v) {
     std::vector<orc::usize> r;
     for (uint64_t x : v) r.push_back(x == UINT64_MAX ? orc::UMAX : (orc::usize)x);
     return r;
   }
-  Poly from_scalar(double x) { return mk(TP::from_scalar(x)); }
-  Poly var(size_t v, double x, size_t len) { return mk(TP::var(v, x, len)); }
+  Poly from_scalar(const Scalar& x) { return mk(TP::from_scalar(A::raw(x))); }
+  Poly var(size_t v, const Scalar& x, size_t len) { return mk(TP::var(v, A::raw(x), len)); }
   Poly var_at_zero(size_t v, size_t len) { return mk(TP::var_at_zero(v, len)); }
-  Poly var_with_degrees(size_t v, double x, const std::vector<uint64_t>& d) { return mk(TP::var_with_degrees_p1(v, x, us(d))); }
+  Poly var_with_degrees(size_t v, const Scalar& x, const std::vector<uint64_t>& d) { return mk(TP::var_with_degrees_p1(v, A::raw(x), us(d))); }
   Poly zero_with(const std::vector<uint64_t>& d) { return mk(TP::zero_with(us(d))); }
-  Poly new_poly(const std::vector<uint64_t>& shape, const std::vector<uint64_t>& degrees, const double* data) {
-    orc::Arr<double> a(us(shape), 0.0);
-    for (size_t i = 0; i < a.data.size(); i++) a.data[i] = data[i];
+  Poly new_poly(const std::vector<uint64_t>& shape, const std::vector<uint64_t>& degrees, const double* data) {   // f64 GenFun constants
+    orc::Arr<T> a(us(shape), A::raw(Scalar(0.0)));
+    for (size_t i = 0; i < a.data.size(); i++) a.data[i] = A::raw(Scalar(data[i]));
+    return mk(TP(std::move(a), us(degrees)));
+  }
+  template <class Q = Scalar, class = std::enable_if_t<!std::is_same<Q, double>::value>>
+  Poly new_poly(const std::vector<uint64_t>& shape, const std::vector<uint64_t>& degrees, const Scalar* data) {
+    orc::Arr<T> a(us(shape), A::raw(Scalar(0.0)));
+    for (size_t i = 0; i < a.data.size(); i++) a.data[i] = A::raw(data[i]);
     return mk(TP(std::move(a), us(degrees)));
   }
   Poly add(const Poly& a, const Poly& b) { return mk(orc::tp_add(*a, *b)); }
@@ -51,21 +90,31 @@ struct OracleBackend {
   Poly truncate_to_degree_p1(const Poly& a, size_t d) { return mk(a->truncate_to_degree_p1(d)); }
   Poly remove_last_variable(const Poly& a) { return mk(a->remove_last_variable()); }
   Poly extend_to_dim(const Poly& a, size_t ndim, size_t d) { return mk(a->extend_to_dim(ndim, d)); }
-  double constant_term(const Poly& a) { return a->constant_term(); }
-  std::vector<double> gather_axis(const Poly& a, size_t v, size_t count) {   // `count` coefficient() calls (:959-965)
-    std::vector<double> out;
+  Scalar constant_term(const Poly& a) { return A::wrap(a->constant_term()); }
+  std::vector<Scalar> gather_axis(const Poly& a, size_t v, size_t count) {   // `count` coefficient() calls (:959-965)
+    std::vector<Scalar> out;
     std::vector<orc::usize> idx(a->num_vars(), 0);
     for (size_t i = 0; i < count; i++) {
       idx.at(v) = i;
-      out.push_back(a->coefficient(idx));
+      out.push_back(A::wrap(a->coefficient(idx)));
     }
     return out;
   }
   size_t num_vars(const Poly& a) { return a->num_vars(); }
   std::vector<uint64_t> array_shape(const Poly& a) { return std::vector<uint64_t>(a->coeffs.shape.begin(), a->coeffs.shape.end()); }
-  std::optional<double> extract_constant(const Poly& a) { return a->extract_constant(); }
-  std::vector<double> to_host(const Poly& a) { return a->coeffs.data; }
+  std::optional<Scalar> extract_constant(const Poly& a) {
+    auto c = a->extract_constant();
+    if (!c) return std::nullopt;
+    return A::wrap(*c);
+  }
+  std::vector<Scalar> to_host(const Poly& a) {
+    std::vector<Scalar> out;
+    for (const T& x : a->coeffs.data) out.push_back(A::wrap(x));
+    return out;
+  }
 };
+using OracleBackend = OracleBackendT<F64Scalar>;
+using IntervalBackend = OracleBackendT<IvScalar>;
 
 }  // namespace
 
@@ -86,6 +135,35 @@ int orc_run_sgcl(const char* source, int64_t limit, int flags, uint64_t unroll, 
     auto res = std::make_unique<orc_sgcl_result>();
     res->r = gfe::run_program(backend, source, opt);
     *out = res.release();
+    return 0;
+  } catch (const std::exception& e) {
+    if (err && err_cap) {
+      std::strncpy(err, e.what(), err_cap - 1);
+      err[err_cap - 1] = '\0';
+    }
+    return 1;
+  }
+}
+// --bounds-style enclosure of the evaluator's direct outputs: the same host logic over TaylorPoly<Interval<F64>>
+// (no simplification pass: its polynomial form stores f64 coefficients).  GenFun constants are the f64 values the f64
+// path uses, taken as point intervals, so this encloses the arithmetic of exactly the DAG the f64 / GPU path evaluates.
+// out: [rest lo, hi, total lo, hi, raw moment 1..4 lo, hi ...] (12 doubles); probs: `limit` pairs [lo, hi].
+int orc_run_sgcl_bounds(const char* source, int64_t limit, uint64_t unroll, double* out12, double* probs_lohi, char* err, size_t err_cap) {
+  try {
+    IntervalBackend backend;
+    gfe::Program program = gfe::parse_program(source);
+    gfe::GfTransformer transformer((size_t)unroll);
+    gfe::GfTranslation tr = transformer.semantics(program);
+    gfe::Evaluator<IntervalBackend> ev(backend);
+    IvS rest = backend.constant_term(ev.eval(tr.rest, std::vector<IvS>(tr.var_info.num_vars(), IvS(0.0)), 1));
+    auto mom = ev.moments_taylor(tr.gf, program.result, tr.var_info, 5);
+    out12[0] = rest.v.lo; out12[1] = rest.v.hi;
+    out12[2] = mom.first.v.lo; out12[3] = mom.first.v.hi;
+    for (size_t i = 0; i < 4; i++) { out12[4 + 2 * i] = mom.second.at(i).v.lo; out12[5 + 2 * i] = mom.second.at(i).v.hi; }
+    if (limit > 0 && probs_lohi) {
+      std::vector<IvS> p = ev.probs_taylor(tr.gf, program.result, tr.var_info, (size_t)limit);
+      for (size_t i = 0; i < (size_t)limit; i++) { probs_lohi[2 * i] = p.at(i).v.lo; probs_lohi[2 * i + 1] = p.at(i).v.hi; }
+    }
     return 0;
   } catch (const std::exception& e) {
     if (err && err_cap) {

@@ -63,6 +63,28 @@ def test_gpu_matches_reference_golden(ctx, rel):
         compare_with_oracle(g, src, opts)
 
 
+def enclosure_fixtures():
+    from helpers import ENCLOSURE_SLOW
+    return [rel for rel in fixtures() if os.path.basename(rel)[:-5] not in ENCLOSURE_SLOW
+            and os.path.getsize(os.path.join(GOLD, rel)) < 50_000]
+
+
+@pytest.mark.parametrize("rel", enclosure_fixtures())
+def test_gpu_results_inside_interval_enclosure(ctx, rel):
+    """north_star check 2, end to end: Z, the raw moments and p(n) computed on the device lie inside the enclosure the
+    oracle computes with the same host logic over TaylorPoly<Interval<F64>> (interval.rs arithmetic, point-interval
+    constants; unpinned -- no reference fixture uses --bounds)."""
+    import genfer_b200
+    from helpers import check_inside_enclosure
+    from oracle import oracle as O
+    src = open(os.path.join(GOLD, rel)).read()
+    opts = genfer_b200.parse_flags(src)
+    g = genfer_b200.run_sgcl(src, limit=opts["limit"], no_probs=opts["no_probs"], no_simplify_gf=opts["no_simplify_gf"],
+                             unroll=opts["unroll"], ctx=ctx)
+    b = O.run_sgcl_bounds(src, limit=len(g.probs), unroll=opts["unroll"])
+    check_inside_enclosure(g, b)
+
+
 def test_gpu_golden_mostly_byte_identical(ctx):
     """How many reports are byte-identical (documentation of the bit-exact share; must not regress below 90 %)."""
     import genfer_b200

@@ -53,3 +53,22 @@ def test_prodigy_burglar_alarm_exact_rational():
     src = open(os.path.join(GOLD, "config", "burglar_alarm.sgcl")).read()
     r = O.run_sgcl(src)
     assert abs(r.normalized_probs[1] - 2969983 / 992160802) <= 1e-15
+
+
+def enclosure_fixtures():
+    from helpers import ENCLOSURE_SLOW
+    return [rel for rel in fixtures() if os.path.basename(rel)[:-5] not in ENCLOSURE_SLOW
+            and os.path.getsize(os.path.join(GOLD, rel)) < 50_000]
+
+
+@pytest.mark.parametrize("rel", enclosure_fixtures())
+def test_f64_results_inside_interval_enclosure(rel):
+    """north_star check 2 on the CPU side: Z, the raw moments and p(n) of the f64 evaluation lie inside the enclosure the
+    same host logic computes over TaylorPoly<Interval<F64>> (the --bounds arithmetic; unpinned: no reference fixture uses
+    --bounds).  The GPU twin is tests/test_gpu_sgcl.py::test_gpu_results_inside_interval_enclosure."""
+    from helpers import check_inside_enclosure
+    src = open(os.path.join(GOLD, rel)).read()
+    opts = parse_flags(src)
+    r = O.run_sgcl(src, limit=opts["limit"], no_probs=opts["no_probs"], no_simplify_gf=opts["no_simplify_gf"], unroll=opts["unroll"])
+    b = O.run_sgcl_bounds(src, limit=len(r.probs), unroll=opts["unroll"])
+    check_inside_enclosure(r, b)
