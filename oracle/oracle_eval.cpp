@@ -4,6 +4,8 @@
 // the CUDA library.  With the reference's operation order and separate multiply/add this reproduces the
 // reference's stdout byte for byte on its .expect fixtures (tests/test_oracle_sgcl.py), which pins both the
 // oracle's arithmetic and the shared host logic.  Never linked into or called from the product path.
+// A second instantiation over TaylorPoly<Interval<f64>> (orc_run_sgcl_bounds) gives the --bounds-style enclosure used by
+// the enclosure tests; PARITY UNPINNED for that one: no reference fixture runs with --bounds.
 #include <cstring>
 #include <memory>
 
