@@ -312,6 +312,8 @@ class TaylorPoly:
     def extend(self, new_size: Sequence[int]): return self._op("gtp_extend", len(new_size), _u64(new_size))
 
     def __repr__(self) -> str:
+        if not self._h or not self.ctx.h:     # context closed: do not call into the library from a traceback formatter
+            return "TaylorPoly(<released>)"
         return f"TaylorPoly({list(self.shape())}, {self.array().tolist()})"
 
 
@@ -398,4 +400,6 @@ class TaylorExpansion:
     __hash__ = None
 
     def __repr__(self):
+        if not self._h or not self.ctx.h:
+            return "TaylorExpansion(<released>)"
         return f"TaylorExpansion({'Constant' if self.is_const() else 'Polynomial'}, {self.coeffs().tolist()})"

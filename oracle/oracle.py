@@ -310,6 +310,8 @@ class TaylorPoly:
     def extend(self, new_size: Sequence[int]): return self._un("extend", _u64(new_size), len(new_size))
 
     def __repr__(self) -> str:
+        if not self._h:      # a constructor that raised: pytest reprs the half-built object while formatting the traceback
+            return "TaylorPoly(<invalid>)"
         return f"TaylorPoly({list(self.shape())}, {self.array().tolist()})"
 
 
@@ -404,6 +406,8 @@ class TaylorExpansion:
     def taylor_expansion_of_coeff(self, n: int): return self._un("te_taylor_expansion_of_coeff", n)
 
     def __repr__(self):
+        if not self._h:
+            return "TaylorExpansion(<invalid>)"
         return f"TaylorExpansion({'Constant' if self.is_const() else 'Polynomial'}, {self.coeffs().tolist()})"
 
 
