@@ -31,6 +31,9 @@ struct GfNode {
   std::vector<size_t> orders; // TaylorPolynomial
   GenFun a, b;                // operands (Subst: a = body, b = replacement)
   std::shared_ptr<const HostPoly> poly;
+  // used_vars of this (immutable) node, filled in on first use: the reference memoises per call (:424-449), which makes
+  // the 12 k `observe` statements of switchpoint re-walk the whole DAG each time (44 % of the host evaluator's profile)
+  mutable size_t used_vars_memo = (size_t)-1;
 };
 
 namespace gf {
@@ -89,8 +92,7 @@ inline bool equal(const GenFun& x, const GenFun& y) {
 // used_vars (:28-47, :424-449): VarRange = max var id + 1; memoised per node like the reference's cache (the DAG is
 // heavily shared: a plain recursion is exponential in the number of if-statements)
 inline size_t used_vars_with(const GenFun& g, std::unordered_map<const GfNode*, size_t>& cache) {
-  auto it = cache.find(g.get());
-  if (it != cache.end()) return it->second;
+  if (g->used_vars_memo != (size_t)-1) return g->used_vars_memo;
   size_t r;
   switch (g->kind) {
     case GfNode::Var: r = g->var + 1; break;
@@ -112,7 +114,8 @@ inline size_t used_vars_with(const GenFun& g, std::unordered_map<const GfNode*, 
     }
     default: r = used_vars_with(g->a, cache); break;
   }
-  cache[g.get()] = r;
+  g->used_vars_memo = r;
+  (void)cache;
   return r;
 }
 inline size_t used_vars(const GenFun& g) {
