@@ -28,6 +28,7 @@ _SIGS = {
     "gtp_ctx_destroy": (None, [vp]),
     "gtp_last_error": (C.c_char_p, [vp]),
     "gtp_ctx_synchronize": (C.c_int, [vp]),
+    "gtp_ctx_trim": (C.c_int, [vp]),
     "gtp_ctx_stream": (vp, [vp]),
     "gtp_ctx_launch_count": (C.c_uint64, [vp]),
     "gtp_ctx_set_fast_mul": (C.c_int, [vp, C.c_int]),

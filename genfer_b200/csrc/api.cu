@@ -1,6 +1,8 @@
 // C ABI of libgenfer_taylor: host-side shape algebra + operator dispatch of TaylorPoly<F64>
 // (multivariate_taylor.rs) over the device kernels.  Shape logic follows the reference line by
 // line (cited); all floating-point work happens on the device -- there is no CPU fallback.
+#include <atomic>
+
 #include "kernels.cuh"
 
 using namespace gtp;
@@ -18,11 +20,14 @@ BufP Ctx::alloc(u64 n) {
   b->cls_bytes = cls;
   b->d = (double*)core->take(cls);
   if (!b->d) {
-    cudaError_t e = cudaMallocAsync((void**)&b->d, cls, stream);
+    auto pool_alloc = [&]() {
+      return core->pool ? cudaMallocFromPoolAsync((void**)&b->d, cls, core->pool, stream) : cudaMallocAsync((void**)&b->d, cls, stream);
+    };
+    cudaError_t e = pool_alloc();
     if (e == cudaErrorMemoryAllocation) {   // give the cached blocks back and try once more
       cudaGetLastError();
       core->trim();
-      e = cudaMallocAsync((void**)&b->d, cls, stream);
+      e = pool_alloc();
     }
     GTP_CUDA(e);
   }
@@ -111,6 +116,16 @@ PolyP new_uninit(Ctx& c, const Shape& shape, const Shape& degrees) {
 PolyP from_values(Ctx& c, const Shape& shape, const Shape& degrees, const double* host) {
   PolyP p = new_uninit(c, shape, degrees);
   GTP_CUDA(cudaMemcpyAsync(p->buf->d, host, prod(shape) * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+  // Pageable sources are staged by the driver before cudaMemcpyAsync returns; a PINNED source is read by the DMA engine
+  // later, so the caller could overwrite or free it before the copy runs.  gtp_from_host promises "data may be reused on
+  // return": wait for the copy when the source is pinned / registered host memory.
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, host) != cudaSuccess) {
+    cudaGetLastError();
+    c.sync();
+  } else if (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged) {
+    c.sync();
+  }
   return p;
 }
 PolyP scalar_poly(Ctx& c, double x, Shape shape_ones, Shape degrees) {
@@ -150,13 +165,25 @@ static bool classify_from_producer(Ctx& c, const gtp_poly& p) {
     }
   }
   if (c.hist) c.t_spin += Ctx::now() - t0;
-  std::atomic_thread_fence(std::memory_order_acquire);
-  p.cls->first = slot->first;
-  p.cls->linear = slot->axis_p1 != 0;      // 1 + the first stored axis of length >= 2 that qualifies (:277-292)
+  // seqlock read: payload between two reads of both sequence copies -- a torn 16-byte device store (not excluded by
+  // the CUDA memory model on every host interconnect) shows up as a sequence mismatch on the second read and is retried
+  double first, m;
+  unsigned axis_p1;
+  for (;;) {
+    std::atomic_thread_fence(std::memory_order_acquire);
+    first = slot->first;
+    m = slot->m;
+    axis_p1 = slot->axis_p1;
+    std::atomic_thread_fence(std::memory_order_acquire);
+    if (ready()) break;
+    if (slot->seq_a > seq) return false;
+  }
+  p.cls->first = first;
+  p.cls->linear = axis_p1 != 0;      // 1 + the first stored axis of length >= 2 that qualifies (:277-292)
   if (p.cls->linear) {
     p.cls->c = p.cls->first;
-    p.cls->m = slot->m;
-    p.cls->v = slot->axis_p1 - 1;
+    p.cls->m = m;
+    p.cls->v = axis_p1 - 1;
   }
   p.cls->known = true;
   c.fused_hits++;
@@ -843,11 +870,23 @@ int gtp_ctx_create(int device, void* cuda_stream, gtp_ctx** out) {
     cudaDeviceProp prop;
     GTP_CUDA(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
-    // keep freed blocks in the stream-ordered pool instead of returning them to the driver
-    cudaMemPool_t pool;
-    GTP_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-    uint64_t thr = UINT64_MAX;
-    GTP_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    // A PRIVATE stream-ordered pool that keeps freed blocks instead of returning them to the driver: the device's default
+    // pool (shared with torch / NCCL allocations of the same process) is left untouched; gtp_ctx_trim() gives the memory back.
+    {
+      cudaMemPoolProps props;
+      memset(&props, 0, sizeof(props));
+      props.allocType = cudaMemAllocationTypePinned;
+      props.handleTypes = cudaMemHandleTypeNone;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = device;
+      if (cudaMemPoolCreate(&c->core->pool, &props) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        GTP_CUDA(cudaMemPoolSetAttribute(c->core->pool, cudaMemPoolAttrReleaseThreshold, &thr));
+      } else {
+        cudaGetLastError();
+        c->core->pool = nullptr;   // fall back to the default pool with its default (release-at-sync) threshold
+      }
+    }
     GTP_CUDA(cudaHostAlloc((void**)&c->rb_host, sizeof(Readback), cudaHostAllocMapped | cudaHostAllocPortable));
     memset(c->rb_host, 0, sizeof(Readback));
     if (cudaHostGetDevicePointer((void**)&c->rb_host_dev, c->rb_host, 0) != cudaSuccess) {
@@ -884,6 +923,13 @@ void gtp_ctx_destroy(gtp_ctx* c) {
 }
 const char* gtp_last_error(gtp_ctx* c) { return c ? c->err.c_str() : "null context"; }
 int gtp_ctx_synchronize(gtp_ctx* c) { return wrap(c, [&] { c->sync(); }); }
+int gtp_ctx_trim(gtp_ctx* c) {   // give the cached free blocks back to the driver (other allocators of the process can use them)
+  return wrap(c, [&] {
+    c->core->trim();
+    c->sync();
+    if (c->core->pool) GTP_CUDA(cudaMemPoolTrimTo(c->core->pool, 0));
+  });
+}
 void* gtp_ctx_stream(gtp_ctx* c) { return c ? (void*)c->stream : nullptr; }
 uint64_t gtp_ctx_launch_count(gtp_ctx* c) { return c ? c->launches : 0; }
 int gtp_ctx_set_fast_mul(gtp_ctx* c, int enabled) {

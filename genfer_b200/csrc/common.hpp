@@ -52,6 +52,7 @@ struct StreamCore {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own = false;
+  cudaMemPool_t pool = nullptr;   // private stream-ordered pool of this context (nullptr: the device's default pool)
   // Size-class cache in front of the stream-ordered pool: every buffer lives on this one stream, so a released block can
   // be handed out again at once.  Requests are rounded up to classes of 1/8 octave, which lets the ever-growing tensors of
   // a Horner / recurrence loop reuse each other's blocks (each new size used to make the pool map fresh physical memory:
@@ -94,6 +95,7 @@ struct StreamCore {
       trim();
       cudaStreamSynchronize(stream);
     }
+    if (pool) cudaMemPoolDestroy(pool);
     if (own && stream) cudaStreamDestroy(stream);
   }
 };

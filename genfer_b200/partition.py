@@ -116,11 +116,23 @@ class PartitionedProduct:
 
 
 def gpu_row_kernel(ctx) -> RowKernel:
-    """Row kernel backed by gtp_mul_rowlist_raw on `ctx` (tensors must live on ctx's device)."""
+    """Row kernel backed by gtp_mul_rowlist_raw on `ctx` (tensors must live on ctx's device).
+
+    Stream contract: the operands (x, the all-gathered y) and `out` are produced / consumed on torch's CURRENT stream,
+    the product is launched on the Context's stream.  When the two are the same stream (create the Context with
+    ``stream=torch.cuda.current_stream().cuda_stream``, as bench.py does) everything is stream-ordered and nothing
+    waits.  When they differ, the kernel is fenced on both sides -- torch's stream is drained before the launch and the
+    Context's stream after it -- so the product can neither read y before the all-gather has finished nor be overtaken by
+    a later all-gather of `out` (correct for any caller; the same-stream set-up is the fast one)."""
 
     def run(xshape, x, yshape, y, rshape, rows, out):
         assert x.is_cuda and y.is_cuda and out.is_cuda, "the f64 Taylor path has no CPU fallback"
         assert x.is_contiguous() and y.is_contiguous() and out.is_contiguous()
+        same = ctx.stream == torch.cuda.current_stream(x.device).cuda_stream
+        if not same:
+            torch.cuda.current_stream(x.device).synchronize()
         ctx.mul_rowlist_raw(xshape, x.data_ptr(), yshape, y.data_ptr(), rshape, rows, out.data_ptr())
+        if not same:
+            ctx.synchronize()
 
     return run

@@ -60,6 +60,10 @@ int gtp_ctx_create(int device, void* cuda_stream, gtp_ctx** out);
 void gtp_ctx_destroy(gtp_ctx* ctx);
 const char* gtp_last_error(gtp_ctx* ctx);
 int gtp_ctx_synchronize(gtp_ctx* ctx);
+/* Returns the context's cached free device blocks to the driver (the context keeps freed blocks in a PRIVATE
+ * stream-ordered pool -- the device's default pool is never modified -- so that other allocators of the process
+ * are only affected by memory this context actually holds).  Synchronises. */
+int gtp_ctx_trim(gtp_ctx* ctx);
 void* gtp_ctx_stream(gtp_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t gtp_ctx_launch_count(gtp_ctx* ctx);
@@ -75,7 +79,9 @@ uint64_t gtp_ctx_launch_count(gtp_ctx* ctx);
 int gtp_ctx_set_fast_mul(gtp_ctx* ctx, int enabled);
 
 /* ---- construction, transfer, metadata ------------------------------------------------------- */
-/* TaylorPoly::new (:33-41): upload `data` (row-major over `shape`, prod(shape) doubles). */
+/* TaylorPoly::new (:33-41): upload `data` (row-major over `shape`, prod(shape) doubles).  `data` may be reused or freed
+ * as soon as the call returns: pageable memory is staged by the driver, and for a pinned / registered source (whose DMA
+ * would run later) the call waits for the copy. */
 int gtp_from_host(gtp_ctx* ctx, int ndim, const uint64_t* shape, const uint64_t* degrees_p1,
                   const double* data, gtp_poly** out);
 /* Same, but wraps an existing device buffer WITHOUT copying or taking ownership (the caller keeps
@@ -156,7 +162,8 @@ int gtp_mul_rowlist_raw(gtp_ctx* ctx, int ndim, const uint64_t* xshape, const do
                         const uint64_t* rows, uint64_t n_rows, double* out_rows);
 /* MAC count of the general product (trip counts of :975-977 and :1002-1004); FLOPs = 2*MACs. */
 double gtp_mul_macs(int ndim, const uint64_t* xshape, const uint64_t* yshape, const uint64_t* rshape);
-/* Which kernel gtp_mul_rows_raw would pick for these shapes: 0 reference-order, 2 2x2-blocked DFMA. */
+/* Which kernel gtp_mul_rows_raw would pick for these shapes: 0 reference-order (or the small-operand stencil kernel),
+ * 2 2x2-blocked DFMA kernel, 3 sliding 1x2 DFMA kernel (dense cube slabs). */
 int gtp_mul_kernel_kind(gtp_ctx* ctx, int ndim, const uint64_t* xshape, const uint64_t* yshape,
                         const uint64_t* rshape);
 /* FP64 pipe microbenchmarks (the roofline denominator): runs `iters` dependent-chain DFMA (kind 0)

@@ -23,15 +23,50 @@ _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 UMAX = 2**64 - 1  # usize::MAX sentinel ("unbounded degree")
 
 
+def _cpu_stamp() -> str:
+    """Identity of the host CPU the library was compiled for (-march=native): model name + ISA flags."""
+    import hashlib
+    model, flags = "", ""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.startswith("model name") and not model:
+                    model = ln.split(":", 1)[1].strip()
+                elif ln.startswith("flags") and not flags:
+                    flags = ln.split(":", 1)[1].strip()
+                if model and flags:
+                    break
+    except OSError:
+        pass
+    return model + " | " + hashlib.sha1(flags.encode()).hexdigest()[:16]
+
+
 def build(force: bool = False) -> str:
-    """Compile liboracle.so with the committed Makefile (gcc, -ffp-contract=off)."""
+    """Compile liboracle.so with the committed Makefile (g++ -O3 -march=native -ffp-contract=off, BASELINE.md's
+    CPU-baseline recipe).  -march=native ties the binary to the build host, so a stamp records the CPU it was built
+    on and a different host (the GPU box) rebuilds once (~30 s) instead of running foreign code."""
+    import fcntl
     import glob
     srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "oracle_eval.cpp", "taylor_oracle.hpp", "Makefile")]
     srcs += glob.glob(os.path.join(_HERE, "..", "genfer_b200", "csrc", "evaluator", "*.hpp"))
-    if (not force and os.path.exists(_LIB_PATH)
-            and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in srcs)):
+    stamp_path = os.path.join(_HERE, "liboracle.stamp")
+    stamp = _cpu_stamp()
+
+    def fresh() -> bool:
+        if not os.path.exists(_LIB_PATH) or not os.path.exists(stamp_path):
+            return False
+        if open(stamp_path).read().strip() != stamp:
+            return False
+        return all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in srcs)
+
+    if not force and fresh():
         return _LIB_PATH
-    subprocess.run(["make", "-C", _HERE, "-B", "liboracle.so"], check=True, capture_output=True)
+    with open(os.path.join(_HERE, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if force or not fresh():
+            subprocess.run(["make", "-C", _HERE, "-B", "liboracle.so"], check=True, capture_output=True)
+            with open(stamp_path, "w") as f:
+                f.write(stamp + "\n")
     return _LIB_PATH
 
 
@@ -41,8 +76,7 @@ _lib = None
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        if not os.path.exists(_LIB_PATH):
-            build()
+        build()
         _lib = C.CDLL(_LIB_PATH)
         _declare(_lib)
     return _lib

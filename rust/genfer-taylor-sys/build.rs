@@ -25,8 +25,14 @@ fn main() {
             .flag("-std=c++17")
             .opt_level(3)
             .include(root.join("include"));
-        for f in ["api.cu", "api_uni.cu", "kernels_elem.cu", "kernels_mul.cu", "kernels_mul_blk.cu", "kernels_mul_slide.cu", "kernels_rec.cu", "univariate.cu"] {
-            let p = csrc.join(f);
+        // every translation unit of the library: csrc/*.cu and csrc/*.cpp (the host evaluator behind gtp_run_sgcl)
+        let mut sources: Vec<PathBuf> = std::fs::read_dir(&csrc)
+            .expect("genfer_b200/csrc")
+            .filter_map(|e| e.ok().map(|e| e.path()))
+            .filter(|p| matches!(p.extension().and_then(|x| x.to_str()), Some("cu") | Some("cpp")))
+            .collect();
+        sources.sort();
+        for p in sources {
             println!("cargo:rerun-if-changed={}", p.display());
             b.file(p);
         }

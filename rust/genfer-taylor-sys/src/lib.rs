@@ -4,21 +4,29 @@
 //! This crate cannot be compiled in the build image (no cargo/rustc there); it is the binding a
 //! genfer maintainer adds, see INTEGRATION.md for the patch to `multivariate_taylor.rs`.
 #![allow(non_camel_case_types)]
-use std::{ffi::CStr, os::raw::{c_char, c_int, c_void}, ptr, rc::Rc};
+use std::{ffi::CStr, os::raw::{c_char, c_int, c_uint, c_void}, ptr, rc::Rc};
 
 pub const GTP_UNBOUNDED: u64 = u64::MAX; // usize::MAX on 64-bit targets
 
 #[repr(C)] pub struct gtp_ctx { _p: [u8; 0] }
 #[repr(C)] pub struct gtp_poly { _p: [u8; 0] }
 #[repr(C)] pub struct gtu_series { _p: [u8; 0] }
+#[repr(C)] pub struct gtp_sgcl_result { _p: [u8; 0] }
 
 extern "C" {
+    // ---- BEGIN GENERATED (tools/gen_rust_externs.py) ----
     pub fn gtp_ctx_create(device: c_int, cuda_stream: *mut c_void, out: *mut *mut gtp_ctx) -> c_int;
     pub fn gtp_ctx_destroy(ctx: *mut gtp_ctx);
     pub fn gtp_last_error(ctx: *mut gtp_ctx) -> *const c_char;
     pub fn gtp_ctx_synchronize(ctx: *mut gtp_ctx) -> c_int;
+    pub fn gtp_ctx_trim(ctx: *mut gtp_ctx) -> c_int;
+    pub fn gtp_ctx_stream(ctx: *mut gtp_ctx) -> *mut c_void;
+    pub fn gtp_ctx_launch_count(ctx: *mut gtp_ctx) -> u64;
+    pub fn gtp_ctx_set_fast_mul(ctx: *mut gtp_ctx, enabled: c_int) -> c_int;
     pub fn gtp_from_host(ctx: *mut gtp_ctx, ndim: c_int, shape: *const u64, degrees_p1: *const u64, data: *const f64, out: *mut *mut gtp_poly) -> c_int;
+    pub fn gtp_from_device(ctx: *mut gtp_ctx, ndim: c_int, shape: *const u64, degrees_p1: *const u64, device_data: *const f64, out: *mut *mut gtp_poly) -> c_int;
     pub fn gtp_to_host(ctx: *mut gtp_ctx, p: *const gtp_poly, out: *mut f64) -> c_int;
+    pub fn gtp_device_ptr(ctx: *mut gtp_ctx, p: *const gtp_poly, out: *mut *const f64) -> c_int;
     pub fn gtp_clone(ctx: *mut gtp_ctx, p: *const gtp_poly, out: *mut *mut gtp_poly) -> c_int;
     pub fn gtp_free(ctx: *mut gtp_ctx, p: *mut gtp_poly);
     pub fn gtp_ndim(p: *const gtp_poly) -> c_int;
@@ -42,18 +50,56 @@ extern "C" {
     pub fn gtp_taylor_expansion_of_coeff(ctx: *mut gtp_ctx, a: *const gtp_poly, v: u64, n: u64, out: *mut *mut gtp_poly) -> c_int;
     pub fn gtp_shift_down(ctx: *mut gtp_ctx, a: *const gtp_poly, v: u64, n: u64, out: *mut *mut gtp_poly) -> c_int;
     pub fn gtp_coefficients_of_term(ctx: *mut gtp_ctx, a: *const gtp_poly, v: u64, order: u64, out: *mut *mut gtp_poly) -> c_int;
+    pub fn gtp_taylor_polynomial(ctx: *mut gtp_ctx, a: *const gtp_poly, v: u64, order: u64, out: *mut *mut gtp_poly) -> c_int;
     pub fn gtp_taylor_polynomial_terms(ctx: *mut gtp_ctx, a: *const gtp_poly, v: u64, orders: *const u64, n_orders: c_int, out: *mut *mut gtp_poly) -> c_int;
     pub fn gtp_subst_var(ctx: *mut gtp_ctx, a: *const gtp_poly, v: u64, subst: *const gtp_poly, out: *mut *mut gtp_poly) -> c_int;
     pub fn gtp_truncate_to_degree_p1(ctx: *mut gtp_ctx, a: *const gtp_poly, degree_p1: u64, out: *mut *mut gtp_poly) -> c_int;
     pub fn gtp_remove_last_variable(ctx: *mut gtp_ctx, a: *const gtp_poly, out: *mut *mut gtp_poly) -> c_int;
     pub fn gtp_extend_to_dim(ctx: *mut gtp_ctx, a: *const gtp_poly, ndim: u64, degree_p1: u64, out: *mut *mut gtp_poly) -> c_int;
+    pub fn gtp_extend(ctx: *mut gtp_ctx, a: *const gtp_poly, ndim: c_int, new_size: *const u64, out: *mut *mut gtp_poly) -> c_int;
     pub fn gtp_constant_term(ctx: *mut gtp_ctx, a: *const gtp_poly, out: *mut f64) -> c_int;
     pub fn gtp_coefficient(ctx: *mut gtp_ctx, a: *const gtp_poly, index: *const u64, n_index: c_int, out: *mut f64) -> c_int;
     pub fn gtp_gather_axis(ctx: *mut gtp_ctx, a: *const gtp_poly, v: u64, count: u64, out: *mut f64) -> c_int;
+    pub fn gtp_extract_constant(ctx: *mut gtp_ctx, a: *const gtp_poly, is_constant: *mut c_int, value: *mut f64) -> c_int;
+    pub fn gtp_extract_linear(ctx: *mut gtp_ctx, a: *const gtp_poly, is_linear: *mut c_int, c: *mut f64, m: *mut f64, v: *mut u64) -> c_int;
     pub fn gtp_is_zero(ctx: *mut gtp_ctx, a: *const gtp_poly, out: *mut c_int) -> c_int;
     pub fn gtp_is_one(ctx: *mut gtp_ctx, a: *const gtp_poly, out: *mut c_int) -> c_int;
+    pub fn gtp_evaluate_all_one(ctx: *mut gtp_ctx, a: *const gtp_poly, out: *mut f64) -> c_int;
     pub fn gtp_eq(ctx: *mut gtp_ctx, a: *const gtp_poly, b: *const gtp_poly, out: *mut c_int) -> c_int;
-    // (gtp_mul_rows_raw / gtp_mul_rowlist_raw / gtu_* omitted here: same pattern, see the header)
+    pub fn gtp_mul_rows_raw(ctx: *mut gtp_ctx, ndim: c_int, xshape: *const u64, x: *const f64, yshape: *const u64, y: *const f64, rshape: *const u64, row_begin: u64, row_step: u64, row_count: u64, out_rows: *mut f64) -> c_int;
+    pub fn gtp_mul_rowlist_raw(ctx: *mut gtp_ctx, ndim: c_int, xshape: *const u64, x: *const f64, yshape: *const u64, y: *const f64, rshape: *const u64, rows: *const u64, n_rows: u64, out_rows: *mut f64) -> c_int;
+    pub fn gtp_mul_macs(ndim: c_int, xshape: *const u64, yshape: *const u64, rshape: *const u64) -> f64;
+    pub fn gtp_mul_kernel_kind(ctx: *mut gtp_ctx, ndim: c_int, xshape: *const u64, yshape: *const u64, rshape: *const u64) -> c_int;
+    pub fn gtp_fp64_peak_probe(ctx: *mut gtp_ctx, kind: c_int, iters: c_int, flops: *mut f64, ms: *mut f64) -> c_int;
+    pub fn gtu_constant(ctx: *mut gtp_ctx, x: f64, out: *mut *mut gtu_series) -> c_int;
+    pub fn gtu_from_coefficients(ctx: *mut gtp_ctx, xs: *const f64, n: u64, out: *mut *mut gtu_series) -> c_int;
+    pub fn gtu_var(ctx: *mut gtp_ctx, x: f64, order: u64, out: *mut *mut gtu_series) -> c_int;
+    pub fn gtu_free(ctx: *mut gtp_ctx, s: *mut gtu_series);
+    pub fn gtu_is_constant(s: *const gtu_series) -> c_int;
+    pub fn gtu_order(s: *const gtu_series) -> u64;
+    pub fn gtu_to_host(ctx: *mut gtp_ctx, s: *const gtu_series, out: *mut f64) -> c_int;
+    pub fn gtu_coeff(ctx: *mut gtp_ctx, s: *const gtu_series, order: u64, out: *mut f64) -> c_int;
+    pub fn gtu_derivative(ctx: *mut gtp_ctx, s: *const gtu_series, order: u64, out: *mut f64) -> c_int;
+    pub fn gtu_add(ctx: *mut gtp_ctx, a: *const gtu_series, b: *const gtu_series, out: *mut *mut gtu_series) -> c_int;
+    pub fn gtu_sub(ctx: *mut gtp_ctx, a: *const gtu_series, b: *const gtu_series, out: *mut *mut gtu_series) -> c_int;
+    pub fn gtu_mul(ctx: *mut gtp_ctx, a: *const gtu_series, b: *const gtu_series, out: *mut *mut gtu_series) -> c_int;
+    pub fn gtu_div(ctx: *mut gtp_ctx, a: *const gtu_series, b: *const gtu_series, out: *mut *mut gtu_series) -> c_int;
+    pub fn gtu_neg(ctx: *mut gtp_ctx, a: *const gtu_series, out: *mut *mut gtu_series) -> c_int;
+    pub fn gtu_exp(ctx: *mut gtp_ctx, a: *const gtu_series, out: *mut *mut gtu_series) -> c_int;
+    pub fn gtu_log(ctx: *mut gtp_ctx, a: *const gtu_series, out: *mut *mut gtu_series) -> c_int;
+    pub fn gtu_pow(ctx: *mut gtp_ctx, a: *const gtu_series, exp: u32, out: *mut *mut gtu_series) -> c_int;
+    pub fn gtu_subst(ctx: *mut gtp_ctx, a: *const gtu_series, subst: *const gtu_series, out: *mut *mut gtu_series) -> c_int;
+    pub fn gtu_taylor_expansion_of_coeff(ctx: *mut gtp_ctx, a: *const gtu_series, n: u64, out: *mut *mut gtu_series) -> c_int;
+    pub fn gtu_eq(ctx: *mut gtp_ctx, a: *const gtu_series, b: *const gtu_series, out: *mut c_int) -> c_int;
+    pub fn gtp_run_sgcl(ctx: *mut gtp_ctx, source: *const c_char, limit: i64, flags: c_int, unroll: u64, out: *mut *mut gtp_sgcl_result, err: *mut c_char, err_cap: usize) -> c_int;
+    pub fn gtp_sgcl_free(r: *mut gtp_sgcl_result);
+    pub fn gtp_sgcl_report(r: *const gtp_sgcl_result) -> *const c_char;
+    pub fn gtp_sgcl_moments(r: *const gtp_sgcl_result, out11: *mut f64);
+    pub fn gtp_sgcl_limit(r: *const gtp_sgcl_result) -> u64;
+    pub fn gtp_sgcl_is_normalized(r: *const gtp_sgcl_result) -> c_int;
+    pub fn gtp_sgcl_probs(r: *const gtp_sgcl_result, unnormalized: *mut f64, normalized: *mut f64);
+    pub fn gtp_sgcl_stats(r: *const gtp_sgcl_result, nodes_evaluated: *mut u64, cache_hits: *mut u64);
+    // ---- END GENERATED ----
 }
 
 /// One CUDA device + stream; `Rc` because genfer is single threaded (`src/main.rs:96-106`).

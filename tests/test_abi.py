@@ -41,6 +41,21 @@ def test_python_binding_table_matches_header(built_lib):
     genfer_b200.load()  # sets restype/argtypes for every symbol; raises if one is absent
 
 
+def test_rust_shim_declares_every_symbol():
+    """rust/genfer-taylor-sys/src/lib.rs is generated from the header (tools/gen_rust_externs.py): no entry point missing,
+    and its build script compiles every translation unit the in-tree build compiles."""
+    import subprocess
+    import sys
+    lib_rs = open(os.path.join(ROOT, "rust", "genfer-taylor-sys", "src", "lib.rs")).read()
+    declared = set(re.findall(r"pub fn (gt[pu]_[a-z0-9_]+)\(", lib_rs))
+    assert sorted(declared) == _declared_symbols()
+    assert subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_rust_externs.py"), "--check"]).returncode == 0
+    from genfer_b200 import build as B
+    csrc = os.path.join(ROOT, "genfer_b200", "csrc")
+    on_disk = sorted(f for f in os.listdir(csrc) if f.endswith((".cu", ".cpp")))
+    assert on_disk == sorted(B.SOURCES), "build.py SOURCES and csrc/ (globbed by build.rs) disagree"
+
+
 def test_mac_count_needs_no_gpu(built_lib):
     """gtp_mul_macs is pure integer work: (D(D+1)/2)^n for dense cubes."""
     import genfer_b200
