@@ -2,6 +2,7 @@
 // (multivariate_taylor.rs) over the device kernels.  Shape logic follows the reference line by
 // line (cited); all floating-point work happens on the device -- there is no CPU fallback.
 #include <atomic>
+#include <cmath>
 
 #include "kernels.cuh"
 
@@ -443,6 +444,8 @@ PolyP poly_div(Ctx& c, const gtp_poly& a0, const gtp_poly& b0, PolyP* recip_cach
                     at->shape, rs, axis);
   } else if (c.fast_mul == 0) {
     launch_div_general(c, at->ptr(), at->shape, bt->ptr(), bt->shape, r->buf->d, rs);   // exact-order mode: wavefront kernel
+  } else if (c.use_wave && launch_rec_wave(c, 0, at->ptr(), at->shape, bt->ptr(), bt->shape, r->buf->d, rs, false)) {
+    // the reference's recurrence (:1170-1191) as one device-resident kernel
   } else {
     // x / y = x (*) (1 / y): the reciprocal series costs 2 products per slice of every non-unit axis (recip_rec), all of
     // them on the product kernels; the wavefront kernel keeps a few thousand threads busy and is slower than one host
@@ -553,19 +556,19 @@ PolyP poly_recip(Ctx& c, const gtp_poly& y, const Shape& ws) {
 }
 
 // exp (:1285-1317) on the sub-views xs[from..] / res[from..] located at xp / rp
-void exp_rec(Ctx& c, const double* xp, const Shape& xs, double* rp, const Shape& rs, size_t from) {
+void exp_rec(Ctx& c, const double* xp, const Shape& xs, double* rp, const Shape& rs, size_t from, const double* seed = nullptr) {
   if (tail_prod(xs, from) == 0) return;
   if (from == rs.size()) {  // res.ndim() == 0
-    launch_scalar_fn(c, 0, xp, rp);
+    launch_scalar_fn(c, 0, xp, rp, seed);
     return;
   }
   u64 n;
   if (one_d_len(rs, from, &n)) {  // exp_1d on the flattened argument
-    launch_exp_1d(c, xp, tail_prod(xs, from), rp, n);
+    launch_exp_1d(c, xp, tail_prod(xs, from), rp, n, seed);
     return;
   }
   const u64 xstr = tail_prod(xs, from + 1), rstr = tail_prod(rs, from + 1);
-  exp_rec(c, xp, xs, rp, rs, from + 1);
+  exp_rec(c, xp, xs, rp, rs, from + 1, seed);
   const u64 xl = xs[from], rl = rs[from];
   if (rl <= 1) return;
   // XS[j-1] = xs[j] * j for j = 1..xl-1  (`x * T::from(j)`, :1309)
@@ -601,21 +604,21 @@ void exp_rec(Ctx& c, const double* xp, const Shape& xs, double* rp, const Shape&
 }
 
 // log (:1335-1386)
-void log_rec(Ctx& c, const double* xp, const Shape& xs, double* rp, const Shape& rs, size_t from) {
+void log_rec(Ctx& c, const double* xp, const Shape& xs, double* rp, const Shape& rs, size_t from, const double* seed = nullptr) {
   if (tail_prod(xs, from) == 0) return;
   if (from == rs.size()) {
-    launch_scalar_fn(c, 1, xp, rp);
+    launch_scalar_fn(c, 1, xp, rp, seed);
     return;
   }
   u64 n;
   if (one_d_len(xs, from, &n)) {  // :1343 -- triggers on the ARGUMENT being 1-d
     u64 rn;
     GTP_CHECK(one_d_len(rs, from, &rn), GTP_ERR_SHAPE, "log: result of a 1-d argument is not 1-d");
-    launch_log_1d(c, xp, tail_prod(xs, from), rp, rn);
+    launch_log_1d(c, xp, tail_prod(xs, from), rp, rn, seed);
     return;
   }
   const u64 xstr = tail_prod(xs, from + 1), rstr = tail_prod(rs, from + 1);
-  log_rec(c, xp, xs, rp, rs, from + 1);
+  log_rec(c, xp, xs, rp, rs, from + 1, seed);
   const u64 xl = xs[from], rl = rs[from];
   if (rl <= 1) return;
   Shape cur_shape = tail(rs, from + 1), x_sub = tail(xs, from + 1);
@@ -693,9 +696,31 @@ PolyP poly_exp_log(Ctx& c, const gtp_poly& a, bool is_log) {
   for (size_t i = 0; i < rs.size(); i++)
     if (a.shape[i] == 1) rs[i] = 1;  // :408-413 / :421-426
   for (u64 x : rs) GTP_CHECK(x != UNB, GTP_ERR_SHAPE, "exp/log of a non-constant series needs bounded degrees");
+  // The one transcendental of the call -- exp / log of the constant term (:1273, :1290, :1321, :1340) -- is taken from
+  // the host's libm whenever the host knows the constant term (small tensors carry it in their cached classification):
+  // that is the function the reference calls, so the seed is bit-identical.  Large tensors use CUDA's <= 1 ulp exp / log
+  // on the device instead of synchronising.
+  double seed_val = 0.0;
+  const double* seed = nullptr;
+  if (a.len() <= 8192) {
+    classify(c, a);
+    seed_val = is_log ? std::log(a.cls->first) : std::exp(a.cls->first);
+    seed = &seed_val;
+  }
+  if (c.use_wave && c.fast_mul != 0) {
+    // N-D (two or more non-unit axes): the whole recurrence in one cooperative kernel.  Small exp calls (the
+    // reference-order product kernel would have served their inner sums) run its exact-order mode and stay bit-identical.
+    int nonunit = 0;
+    for (u64 x : rs) nonunit += x > 1;
+    const bool small = mul_macs(a.shape, rs, rs) < DFMA_MIN_MACS;
+    if (nonunit >= 2) {
+      PolyP r = new_uninit(c, rs, a.degrees);
+      if (launch_rec_wave(c, is_log ? 2 : 1, a.ptr(), a.shape, nullptr, Shape(), r->buf->d, rs, !is_log && small, seed)) return r;
+    }
+  }
   PolyP r = new_zeros(c, rs, a.degrees);
-  if (is_log) log_rec(c, a.ptr(), a.shape, r->buf->d, rs, 0);
-  else exp_rec(c, a.ptr(), a.shape, r->buf->d, rs, 0);
+  if (is_log) log_rec(c, a.ptr(), a.shape, r->buf->d, rs, 0, seed);
+  else exp_rec(c, a.ptr(), a.shape, r->buf->d, rs, 0, seed);
   return r;
 }
 
@@ -940,6 +965,7 @@ int gtp_ctx_set_fast_mul(gtp_ctx* c, int enabled) {
   c->use_slide = (enabled & 16) == 0;
   c->fuse_mul_linear = (enabled & 128) == 0;
   c->use_stencil = (enabled & 256) == 0;
+  c->use_wave = (enabled & 1024) == 0;
   c->stencil_v4 = (enabled & 512) == 0;
   c->slide_tile = ((enabled >> 5) & 3) == 1 ? 4 : (((enabled >> 5) & 3) == 2 ? 8 : 0);   // A/B measurements
   enabled &= 3;

@@ -192,11 +192,19 @@ void launch_div_axis(Ctx& ctx, const double* x, const double* y, double* r, u64 
 // General N-D division by total-degree wavefronts.
 void launch_div_general(Ctx& ctx, const double* x, const Shape& xs, const double* y, const Shape& ys,
                         double* r, const Shape& rs);
+// Device-resident N-D recurrences (kernels_wave.cu): general division (op 0, y = divisor), exp (1), log (2) as ONE
+// cooperative kernel walking the leaf levels.  `exact`: exp only -- reference summation order, bit-identical.
+// Returns false when the shapes are outside its domain (fewer than two non-unit result axes, ...).
+bool launch_rec_wave(Ctx& ctx, int op, const double* x, const Shape& xs, const double* y, const Shape& ys, double* r,
+                     const Shape& rs, bool exact, const double* seed = nullptr);
 // 1-D exp / log recurrences (exp_1d :1271-1283, log_1d :1319-1333) on contiguous vectors
-void launch_exp_1d(Ctx& ctx, const double* x, u64 xlen, double* r, u64 n);
-void launch_log_1d(Ctx& ctx, const double* x, u64 xlen, double* r, u64 n);
+// `seed` (host pointer or nullptr): exp / log of the constant term x[0] evaluated by the host's libm, used when the host
+// already knows x[0] -- the reference calls the same libm (number/f64.rs:53-62), so the result is then bit-identical;
+// nullptr: CUDA's exp / log (<= 1 ulp) on the device, no synchronisation.
+void launch_exp_1d(Ctx& ctx, const double* x, u64 xlen, double* r, u64 n, const double* seed = nullptr);
+void launch_log_1d(Ctx& ctx, const double* x, u64 xlen, double* r, u64 n, const double* seed = nullptr);
 // r[0] = exp(x[0]) / log(x[0])  (scalar leaf :1289-1291, :1339-1341)
-void launch_scalar_fn(Ctx& ctx, int fn, const double* x, double* r);
+void launch_scalar_fn(Ctx& ctx, int fn, const double* x, double* r, const double* seed = nullptr);
 // out[i] = in[i] * k   or   in[i] / k   (k an integer-valued double; :1309, :1315, :1364, :1374, :1384)
 void launch_scale_const(Ctx& ctx, const double* in, double* out, u64 n, double k, bool divide);
 // rows j = 0..rows-1 of `in` (row length `inner`) scaled by (j + j0):  out[j,:] = in[j,:] * (j+j0)

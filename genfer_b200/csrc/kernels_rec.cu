@@ -196,12 +196,14 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
   }
   return t;  // valid in thread 0
 }
+// `seed`: exp / log of the constant term evaluated by the host's libm when the host knows the constant term (bit-identical
+// to the reference's f64::exp / ln, number/f64.rs:53-62); otherwise CUDA's exp / log (<= 1 ulp) on the device.
 __global__ void __launch_bounds__(REC_THREADS) k_exp_1d(const double* __restrict__ x, u64 xlen, double* r, u64 n,
-                                                       double* scratch) {
+                                                       double* scratch, int has_seed, double seed) {
   __shared__ double sh[REC_THREADS / 32];
   // scratch[j] = x[j] * j   (the reference's `xs[j] * T::from(j)` factor)
   for (u64 j = threadIdx.x; j < xlen; j += REC_THREADS) scratch[j] = __dmul_rn(x[j], (double)(unsigned)j);
-  if (threadIdx.x == 0) r[0] = exp(x[0]);
+  if (threadIdx.x == 0) r[0] = has_seed ? seed : exp(x[0]);
   __syncthreads();
   for (u64 k = 1; k < n; k++) {
     u64 hi = xlen < k + 1 ? xlen : k + 1;
@@ -222,11 +224,11 @@ __global__ void __launch_bounds__(REC_THREADS) k_exp_1d(const double* __restrict
   }
 }
 __global__ void __launch_bounds__(REC_THREADS) k_log_1d(const double* __restrict__ x, u64 xlen, double* r, u64 n,
-                                                       double* scratch) {
+                                                       double* scratch, int has_seed, double seed) {
   __shared__ double sh[REC_THREADS / 32];
   // scratch[j] = r[j] * j, filled as coefficients become final
   if (threadIdx.x == 0) {
-    r[0] = log(x[0]);
+    r[0] = has_seed ? seed : log(x[0]);
     scratch[0] = 0.0;
   }
   __syncthreads();
@@ -254,21 +256,23 @@ __global__ void __launch_bounds__(REC_THREADS) k_log_1d(const double* __restrict
     __syncthreads();
   }
 }
-void launch_exp_1d(Ctx& ctx, const double* x, u64 xlen, double* r, u64 n) {
+void launch_exp_1d(Ctx& ctx, const double* x, u64 xlen, double* r, u64 n, const double* seed) {
   if (n == 0) return;
   BufP scratch = ctx.alloc(std::max<u64>(xlen, 1));
-  GTP_LAUNCH(ctx, k_exp_1d, 1, REC_THREADS, 0, x, xlen, r, n, scratch->d);
+  GTP_LAUNCH(ctx, k_exp_1d, 1, REC_THREADS, 0, x, xlen, r, n, scratch->d, seed ? 1 : 0, seed ? *seed : 0.0);
 }
-void launch_log_1d(Ctx& ctx, const double* x, u64 xlen, double* r, u64 n) {
+void launch_log_1d(Ctx& ctx, const double* x, u64 xlen, double* r, u64 n, const double* seed) {
   if (n == 0) return;
   BufP scratch = ctx.alloc(std::max<u64>(n, 1));
-  GTP_LAUNCH(ctx, k_log_1d, 1, REC_THREADS, 0, x, xlen, r, n, scratch->d);
+  GTP_LAUNCH(ctx, k_log_1d, 1, REC_THREADS, 0, x, xlen, r, n, scratch->d, seed ? 1 : 0, seed ? *seed : 0.0);
 }
 
-__global__ void k_scalar_fn(int fn, const double* x, double* r) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) r[0] = (fn == 0) ? exp(x[0]) : log(x[0]);
+__global__ void k_scalar_fn(int fn, const double* x, double* r, int has_seed, double seed) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) r[0] = has_seed ? seed : ((fn == 0) ? exp(x[0]) : log(x[0]));
 }
-void launch_scalar_fn(Ctx& ctx, int fn, const double* x, double* r) { GTP_LAUNCH(ctx, k_scalar_fn, 1, 32, 0, fn, x, r); }
+void launch_scalar_fn(Ctx& ctx, int fn, const double* x, double* r, const double* seed) {
+  GTP_LAUNCH(ctx, k_scalar_fn, 1, 32, 0, fn, x, r, seed ? 1 : 0, seed ? *seed : 0.0);
+}
 
 __global__ void __launch_bounds__(256) k_scale_const(const double* __restrict__ in, double* __restrict__ out, u64 n, double k, int divide) {
   u64 stride = (u64)gridDim.x * blockDim.x;

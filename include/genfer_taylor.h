@@ -72,7 +72,8 @@ uint64_t gtp_ctx_launch_count(gtp_ctx* ctx);
  * tiny products (tests).  A/B bits: +4 evenly dealt instead of folded item tables (blocked kernel), +8 octet tables
  * (experimental), +16 sliding kernel off, +32 / +64 force the plane-tiled sliding plan with 4 / 8 planes per slab,
  * +128 mul_linear as the reference's composition instead of the one-pass kernel, +256 small-operand stencil kernel off,
- * +512 stencil kernel with one instead of four coefficients per thread.
+ * +512 stencil kernel with one instead of four coefficients per thread, +1024 device-resident N-D div / exp / log
+ * recurrences off (host loops of product launches).
  * Environment (read at gtp_ctx_create): GTP_LAUNCH_HIST=1 prints per-kernel launch counts and host-time shares when the
  * context is destroyed; GTP_NO_SCALAR_POOL=1 / GTP_NO_FUSED_CLS=1 switch the host-written scalar slots / the fused
  * classification off. */
