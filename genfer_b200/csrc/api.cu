@@ -804,7 +804,26 @@ PolyP poly_subst_var(Ctx& c, const gtp_poly& self, u64 v, const gtp_poly& subst)
   for (size_t a = 0; a < ext.size(); a++) ext[a] = std::min(cs.shape[a], d[a]);
   GTP_CHECK(d[v] >= 1, GTP_ERR_SHAPE, "subst_var: zero degree along the substituted axis");
   ext[v] = 1;
+  gtp_poly sb = subst;   // the substitution on the common axes (trailing unit axes, like broadcast :832-852)
+  sb.shape.resize(cs.shape.size(), 1);
   for (u64 i = cs.shape[v]; i-- > 0;) {
+    // Once res has grown past a scalar the rest of the loop is one fused kernel (kernels_horner.cu).  Mul's linear fast
+    // path (:1052-1061) gives the general product's values but clips the stored shape to the other operand's (+1 along the
+    // axis) when the linear operand carries explicit zeros: the fused loop is entered only with a non-linear Horner value
+    // and a substitution that is non-linear or compactly linear (stored shape 2 along its axis, 1 elsewhere), where the
+    // two paths also agree on the stored shape.
+    if (c.use_horner && c.fast_mul != 0 && res->len() > 1 && sb.len() >= 2 && sb.len() <= 32 && res->shape.size() == cs.shape.size()) {
+      bool subst_ok = !subst.cls->linear || sb.len() == 2;
+      if (subst_ok) {
+        classify(c, *res);
+        if (!res->cls->linear) {
+          BufP ob;
+          Shape os;
+          if (launch_horner(c, cs.ptr(), cs.shape, v, d, sb.ptr(), sb.shape, res->ptr(), res->shape, i, &ob, &os))
+            return make_poly(ob, 0, os, d);
+        }
+      }
+    }
     lo[v] = i;
     PolyP slice = copy_box(c, cs, lo, ext, d);
     PolyP prod_ = poly_mul(c, *res, subst);
@@ -966,6 +985,7 @@ int gtp_ctx_set_fast_mul(gtp_ctx* c, int enabled) {
   c->fuse_mul_linear = (enabled & 128) == 0;
   c->use_stencil = (enabled & 256) == 0;
   c->use_wave = (enabled & 1024) == 0;
+  c->use_horner = (enabled & 2048) == 0;
   c->stencil_v4 = (enabled & 512) == 0;
   c->slide_tile = ((enabled >> 5) & 3) == 1 ? 4 : (((enabled >> 5) & 3) == 2 ? 8 : 0);   // A/B measurements
   enabled &= 3;

@@ -197,6 +197,11 @@ void launch_div_general(Ctx& ctx, const double* x, const Shape& xs, const double
 // Returns false when the shapes are outside its domain (fewer than two non-unit result axes, ...).
 bool launch_rec_wave(Ctx& ctx, int op, const double* x, const Shape& xs, const double* y, const Shape& ys, double* r,
                      const Shape& rs, bool exact, const double* seed = nullptr);
+// Fused Horner loop of subst_var (kernels_horner.cu): steps i_top .. 0 of `res = res * subst + self.slice(v, i)` in ONE
+// cooperative kernel, for a substitution of 2..32 coefficients.  Bit-identical to the per-operator steps.  false: outside
+// its domain (the caller continues step by step).
+bool launch_horner(Ctx& ctx, const double* self, const Shape& self_shape, u64 v, const Shape& d, const double* subst,
+                   const Shape& sshape, const double* res, const Shape& rshape, u64 i_top, BufP* out_buf, Shape* out_shape);
 // 1-D exp / log recurrences (exp_1d :1271-1283, log_1d :1319-1333) on contiguous vectors
 // `seed` (host pointer or nullptr): exp / log of the constant term x[0] evaluated by the host's libm, used when the host
 // already knows x[0] -- the reference calls the same libm (number/f64.rs:53-62), so the result is then bit-identical;

@@ -27,6 +27,7 @@
 // the reference-order product kernel it replaces.
 #include <map>
 
+#include "device_sync.cuh"
 #include "kernels.cuh"
 
 namespace gtp {
@@ -60,21 +61,6 @@ __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
-}
-
-__device__ __forceinline__ double ldcg(const double* p) { return __ldcg(p); }
-
-__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& phase) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    phase++;
-    __threadfence();
-    atomicAdd(bar, 1u);
-    const unsigned target = phase * gridDim.x;
-    while (*(volatile unsigned*)bar < target) { }
-    __threadfence();
-  }
-  __syncthreads();
 }
 
 // One set of pairs of a leaf: index variables u_i in [lo_i, lo_i + ext_i), first axis slowest.

@@ -367,6 +367,57 @@ def test_univariate_matches_oracle(G, n):
 
 
 # ---------------------------------------------------------------------------------------------
+# fused Horner loop (kernels_horner.cu): subst_var with a substitution of <= 32 coefficients, the inner loop of the
+# compound distributions / assignments of real programs (multivariate_taylor.rs:569-579) -- bit-identical to the
+# reference's per-step Mul + Add, in a handful of launches instead of three per slice
+# ---------------------------------------------------------------------------------------------
+HORNER_CASES = [  # (self shape, degrees, substituted axis, subst shape)
+    ((9, 8, 7), (12, 11, 10), 2, (2, 1, 2)), ((9, 8, 7), (12, 11, 10), 0, (2, 2, 1)), ((20, 6), (24, 9), 0, (2, 2)),
+    ((6, 20), (9, 24), 1, (1, 3)), ((6, 20), (9, 24), 1, (3, 1)), ((30,), (40,), 0, (3,)), ((5, 4, 3, 6), (6, 6, 6, 6), 3, (2, 1, 1, 2)),
+    ((40, 50, 45), (60, 60, 60), 2, (2, 1, 2)), ((7, 5), (7, 5), 1, (4, 5)), ((12, 3), (30, 30), 1, (2, 3)),
+    ((33, 1, 9), (40, 5, 12), 2, (1, 2, 2))]
+
+
+@pytest.mark.parametrize("shape,deg,v,sshape", HORNER_CASES)
+def test_fused_horner_is_bit_exact(G, shape, deg, v, sshape):
+    rng = np.random.default_rng(sum(shape) + v)
+    a, sub = rng.standard_normal(shape), rng.standard_normal(sshape)
+    g, o = both(G, a, deg)
+    gs, os_ = both(G, sub, deg)
+    ctx = g.ctx
+    l0 = ctx.launch_count
+    got = g.subst_var(v, gs)
+    launches = ctx.launch_count - l0
+    assert_same(got, o.subst_var(v, os_))
+    assert launches <= 12, launches            # a few per-operator steps until res is non-scalar, then ONE kernel
+    # A/B: the per-operator path gives the same bits
+    ctx.set_fast_mul(1 + 2048)
+    try:
+        assert_same(g.subst_var(v, gs), o.subst_var(v, os_))
+    finally:
+        ctx.set_fast_mul(1)
+
+
+def test_fused_horner_with_zero_slices_and_scalar_slices(G):
+    """Top slices that are exactly zero keep res a scalar zero for a while (Mul's is_zero path, :1021-1023); a 1-d self
+    has scalar slices (Add's scalar path, :862-865)."""
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((6, 9))
+    a[:, 6:] = 0.0
+    sub = rng.standard_normal((2, 2))
+    g, o = both(G, a, (10, 12))
+    gs, os_ = both(G, sub, (10, 12))
+    assert_same(g.subst_var(1, gs), o.subst_var(1, os_))
+    b = rng.standard_normal((25,))
+    b[-3:] = 0.0
+    g, o = both(G, b, (30,))
+    gs, os_ = both(G, np.array([0.25, -1.5, 0.75]), (30,))
+    assert_same(g.subst_var(0, gs), o.subst_var(0, os_))
+    gs2, os2 = both(G, rng.standard_normal((1, 3)), (30, 8))       # substitution with more variables than self
+    assert_same(g.subst_var(0, gs2), o.subst_var(0, os2))
+
+
+# ---------------------------------------------------------------------------------------------
 # device-resident recurrences (kernels_wave.cu): the reference's div / exp / log recurrences (:1162-1192, :1285-1386)
 # as ONE cooperative kernel per call -- 1e-12 against the oracle at sizes where the old host loops needed hundreds of
 # launches (and the old reciprocal-series division lost four digits), and at most 4 launches per call
