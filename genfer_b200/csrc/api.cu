@@ -986,6 +986,7 @@ int gtp_ctx_set_fast_mul(gtp_ctx* c, int enabled) {
   c->use_stencil = (enabled & 256) == 0;
   c->use_wave = (enabled & 1024) == 0;
   c->use_horner = (enabled & 2048) == 0;
+  c->use_axis = (enabled & 4096) == 0;
   c->stencil_v4 = (enabled & 512) == 0;
   c->slide_tile = ((enabled >> 5) & 3) == 1 ? 4 : (((enabled >> 5) & 3) == 2 ? 8 : 0);   // A/B measurements
   enabled &= 3;

@@ -252,7 +252,10 @@ bool launch_horner(Ctx& ctx, const double* self, const Shape& self_shape, u64 v,
   }
   if (per_sm < 0) return false;
   const u64 want = (final_total + HN_T - 1) / HN_T;
-  const unsigned grid = (unsigned)std::max<u64>(1, std::min<u64>(want, (u64)std::min(per_sm, 4) * ctx.sm_count));
+  // small and mid-size tensors are barrier-bound (a step is ~1 us of L2 traffic): one CTA per SM keeps the barrier short;
+  // HBM-sized tensors want every resident CTA for loads in flight
+  const int ctas_per_sm = final_total >= (1u << 21) ? std::min(per_sm, 4) : (final_total >= (1u << 18) ? std::min(per_sm, 2) : 1);
+  const unsigned grid = (unsigned)std::max<u64>(1, std::min<u64>(want, (u64)ctas_per_sm * ctx.sm_count));
   void* args[] = {(void*)&p};
   const double t0 = ctx.hist ? Ctx::now() : 0.0;
   GTP_CUDA(cudaLaunchCooperativeKernel((const void*)k_horner, dim3(grid), dim3(HN_T), args, 0, ctx.stream));

@@ -134,6 +134,7 @@ bool blk_mul_applicable(const Ctx& ctx, const MulArgs& a);
 void launch_mul_blk(Ctx& ctx, const MulArgs& a);
 bool slide_mul_applicable(const Ctx& ctx, const MulArgs& a);
 void launch_mul_slide(Ctx& ctx, const MulArgs& a);
+bool launch_mul_axis(Ctx& ctx, const MulArgs& a);   // kernels_mul_axis.cu
 
 // 0: reference-order kernel, 2: 2x2-blocked DFMA kernel (kernels_mul_blk.cu), 3: sliding 1x2 DFMA kernel for dense
 // cube slabs (kernels_mul_slide.cu).  (1 was the cube-16-only kernel of
@@ -476,6 +477,7 @@ void launch_mul(Ctx& ctx, const MulArgs& a_in) {
     return;
   }
   if (ctx.fast_mul && ctx.use_stencil && launch_mul_stencil(ctx, a)) return;   // bit-exact, HBM-bound small-operand products
+  if (ctx.fast_mul && ctx.use_axis && launch_mul_axis(ctx, a)) return;         // bit-exact, 1-d operand x N-d tensor
   if (a.rows.empty()) {
     launch_mul_ordered(ctx, a);
     return;

@@ -73,7 +73,8 @@ uint64_t gtp_ctx_launch_count(gtp_ctx* ctx);
  * (experimental), +16 sliding kernel off, +32 / +64 force the plane-tiled sliding plan with 4 / 8 planes per slab,
  * +128 mul_linear as the reference's composition instead of the one-pass kernel, +256 small-operand stencil kernel off,
  * +512 stencil kernel with one instead of four coefficients per thread, +1024 device-resident N-D div / exp / log
- * recurrences off (host loops of product launches), +2048 fused Horner loop of subst_var off (three launches per step).
+ * recurrences off (host loops of product launches), +2048 fused Horner loop of subst_var off (three launches per step),
+ * +4096 axis-convolution kernel (1-d operand x N-d tensor) off.
  * Environment (read at gtp_ctx_create): GTP_LAUNCH_HIST=1 prints per-kernel launch counts and host-time shares when the
  * context is destroyed; GTP_NO_SCALAR_POOL=1 / GTP_NO_FUSED_CLS=1 switch the host-written scalar slots / the fused
  * classification off. */

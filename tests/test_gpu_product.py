@@ -131,6 +131,27 @@ def test_sliding_kernel_ragged_leading_axes(ctx, mode):
     np.testing.assert_allclose(got, ref, rtol=1e-11, atol=1e-12)
 
 
+AXIS_CASES = [((282, 1), (282, 282), (282, 282)), ((1, 282), (282, 282), (282, 282)), ((247, 247), (36, 1), (247, 247)),
+              ((161, 161), (1, 84), (161, 161)), ((40, 1, 1), (30, 20, 10), (50, 20, 10)), ((30, 20, 10), (1, 45, 1), (30, 40, 10)),
+              ((1, 1, 300), (7, 5, 200), (7, 5, 260)), ((9, 200), (1, 300), (9, 499)), ((500,), (1,), (500,)), ((64, 64), (64, 1), (100, 64)),
+              ((5, 1, 70, 1), (5, 3, 70, 9), (9, 3, 139, 9))]
+
+
+@pytest.mark.parametrize("xs,ys,rs", AXIS_CASES)
+def test_axis_convolution_kernel_is_bit_exact(ctx, xs, ys, rs):
+    """1-d operand x N-d tensor (kernels_mul_axis.cu): bit-identical to the oracle's reference order, either operand order,
+    axis first / middle / last, results shorter and longer than the operands."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(sum(xs) + sum(ys))
+    x, y = rng.standard_normal(xs), rng.standard_normal(ys)
+    ref = O.mul_raw(x, y, rs)
+    got = gpu_mul_raw(ctx, x, y, rs, fast=True)
+    assert np.array_equal(got.view(np.uint64), ref.view(np.uint64))
+    ref = O.mul_raw(y, x, rs)
+    got = gpu_mul_raw(ctx, y, x, rs, fast=True)
+    assert np.array_equal(got.view(np.uint64), ref.view(np.uint64))
+
+
 @pytest.mark.parametrize("n,d", [(4, 12), (4, 16), (5, 12), (5, 16), (4, 8), (4, 24), (4, 10)])
 def test_kernel_selection(ctx, n, d):
     """Dense cube slabs take the sliding kernel (3): whole slabs when they give >= 16 folded lanes and fit in shared
