@@ -38,6 +38,7 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 METRIC = "truncated N-D Taylor product FP64 GFLOP/s"
+KERNEL_NAMES = {2: "k_mul_blk", 3: "k_mul_slide", 6: "k_mul_blk on zero-extended operands", 7: "k_mul_slide on zero-extended operands"}
 UNIT = "GFLOP/s"
 
 
@@ -113,7 +114,9 @@ def run_sweep(ctx, torch, peak_tf: float, cpu_budget_gmac: float):
     parity sample that includes leading rows k0 > 0."""
     import genfer_b200
     out = []
-    for n, d in ((4, 32), (5, 16), (6, 12), (5, 24)):
+    # (4,32) .. (5,24): BASELINE's sweep; (4,27), (4,31), (5,17): odd cube edges as evaluation produces them
+    # (limit + 1 + sum of orders), zero-extended to the DFMA kernels' extents
+    for n, d in ((4, 32), (5, 16), (6, 12), (5, 24), (4, 27), (4, 31), (5, 17)):
         shape = (d,) * n
         xh, yh = synth_inputs(n, d)
         dx, dy = torch.from_numpy(xh).cuda(), torch.from_numpy(yh).cuda()
@@ -136,7 +139,7 @@ def run_sweep(ctx, torch, peak_tf: float, cpu_budget_gmac: float):
         torch.cuda.synchronize()
         ms = a.elapsed_time(b) / reps
         tf = 2.0 * full_macs(n, d) / (ms * 1e-3) / 1e12
-        rec = {"workload": f"{n}x{d}", "coefficients": d ** n, "kernel": {2: "k_mul_blk", 3: "k_mul_slide"}.get(kind, "k_mul_ordered"),
+        rec = {"workload": f"{n}x{d}", "coefficients": d ** n, "kernel": KERNEL_NAMES.get(kind, "k_mul_ordered"),
                "ms": ms, "tflops": tf, "frac_of_fp64_peak": tf / peak_tf, "first_call_ms": first_ms}
         if cpu_budget_gmac > 0:
             got = dz.cpu().numpy()
@@ -445,7 +448,7 @@ def run_ours(args):
             traffic = json.load(open(tpath)).get(args.workload, {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "fp64", "kernel": {2: "k_mul_blk", 3: "k_mul_slide"}.get(kind, "k_mul_ordered"),
+    roofline = {"bound": "fp64", "kernel": KERNEL_NAMES.get(kind, "k_mul_ordered"),
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "FP64 FMA pipe measured live by gtp_fp64_peak_probe (8 independent DFMA chains/thread, all SMs); "

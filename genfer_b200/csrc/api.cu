@@ -987,6 +987,7 @@ int gtp_ctx_set_fast_mul(gtp_ctx* c, int enabled) {
   c->use_wave = (enabled & 1024) == 0;
   c->use_horner = (enabled & 2048) == 0;
   c->use_axis = (enabled & 4096) == 0;
+  c->use_pad = (enabled & 8192) == 0;
   c->stencil_v4 = (enabled & 512) == 0;
   c->slide_tile = ((enabled >> 5) & 3) == 1 ? 4 : (((enabled >> 5) & 3) == 2 ? 8 : 0);   // A/B measurements
   enabled &= 3;
@@ -1358,7 +1359,7 @@ int gtp_mul_kernel_kind(gtp_ctx* c, int ndim, const uint64_t* xs, const uint64_t
   m.ys = to_shape(ys, ndim);
   m.rs = to_shape(rs, ndim);
   m.row_count = m.rs.empty() ? 1 : m.rs[0];
-  return mul_kernel_kind(*c, m);
+  return mul_plan_kind(*c, m);
 }
 int gtp_fp64_peak_probe(gtp_ctx* c, int kind, int iters, double* flops, double* ms) {
   return wrap(c, [&] { fp64_peak_probe(*c, kind, iters, flops, ms); });

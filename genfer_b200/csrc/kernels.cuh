@@ -174,6 +174,7 @@ struct MulArgs {
 };
 void launch_mul(Ctx& ctx, const MulArgs& a);
 int mul_kernel_kind(const Ctx& ctx, const MulArgs& a);
+int mul_plan_kind(const Ctx& ctx, const MulArgs& a);   // incl. the zero-extended plans (6 / 7)
 double mul_macs(const Shape& xs, const Shape& ys, const Shape& rs);
 double args_macs(const MulArgs& a);   // MACs of the rows this launch computes
 // Products below this many MACs stay on the reference-order kernel (bit-exact, and launch-bound anyway); above it the

@@ -139,6 +139,20 @@ bool launch_mul_axis(Ctx& ctx, const MulArgs& a);   // kernels_mul_axis.cu
 // 0: reference-order kernel, 2: 2x2-blocked DFMA kernel (kernels_mul_blk.cu), 3: sliding 1x2 DFMA kernel for dense
 // cube slabs (kernels_mul_slide.cu).  (1 was the cube-16-only kernel of
 // the first round; the blocked kernel with folded tables superseded it.)
+static int pad_plan(const Ctx& ctx, const MulArgs& a, MulArgs* out_best);
+// what launch_mul() will run -- 0: reference-order family (reference-order kernel, small-operand stencil, axis convolution:
+// all bit-exact), 2 / 3: blocked / sliding DFMA kernel, 6 / 7: the same after zero-extending odd extents
+int mul_plan_kind(const Ctx& ctx, const MulArgs& a) {
+  const int k = mul_kernel_kind(ctx, a);
+  if (k || !ctx.fast_mul) return k;
+  if (ctx.use_stencil && std::min(prod(a.xs), prod(a.ys)) <= (u64)32 && std::max(prod(a.xs), prod(a.ys)) >= 4096) return 0;
+  int nonunit_x = 0, nonunit_y = 0;
+  for (int d = 0; d < a.ndim; d++) { nonunit_x += a.xs[d] > 1; nonunit_y += a.ys[d] > 1; }
+  if (ctx.use_axis && (nonunit_x == 1) != (nonunit_y == 1)) return 0;   // axis convolution (bit-exact)
+  MulArgs best;
+  const int pk = pad_plan(ctx, a, &best);
+  return pk ? pk + 4 : 0;
+}
 int mul_kernel_kind(const Ctx& ctx, const MulArgs& a) {
   if (!ctx.fast_mul) return 0;
   if ((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.y)) & 15u) return 0;  // cp.async 16-byte staging
@@ -452,6 +466,86 @@ static bool launch_mul_stencil(Ctx& ctx, const MulArgs& a) {
   return true;
 }
 
+// ------------------------------------------------------------------------------------------
+// Shape cliff: the DFMA kernels want the last axis equal in X, Y and Z and a multiple of an even chunk (8..16); the sliding
+// kernel also equal, even / multiple-of-4 plane and row counts.  Evaluation cubes have edge limit + 1 + sum(orders)
+// (generating_function.rs:628-657, 756-763) -- 27, 31, 17 ... -- and used to fall to the reference-order kernel (~0.15
+// TFLOP/s, 160x slower).  Zero-extending the operands to the next supported extents does not change any coefficient of
+// the truncated product (absent coefficients ARE zeros, multivariate_taylor.rs:15-18), so such products are padded (two
+// gather passes), multiplied by the DFMA kernels and cropped (one pass): three HBM passes against a compute-bound
+// product, at the price of the padded multiply-adds (bounded below).
+// ------------------------------------------------------------------------------------------
+static u64 pad_chunkable(u64 l) {
+  for (u64 c = l;; c++)
+    for (u64 lt : {16, 14, 12, 10, 8})
+      if (c % lt == 0) return c;
+}
+// 0: no padded plan; 2 / 3: zero-extend and run the blocked / sliding kernel on `best`
+static int pad_plan(const Ctx& ctx, const MulArgs& a, MulArgs* out_best) {
+  const int nd = a.ndim;
+  if (nd < 3 || a.accumulate || !ctx.use_pad) return 0;
+  const double macs = args_macs(a);
+  if (macs < 4.0 * DFMA_MIN_MACS) return 0;
+  auto padded = [&](bool slide) {
+    MulArgs m = a;
+    m.rs[nd - 1] = pad_chunkable(a.rs[nd - 1]);
+    m.xs[nd - 1] = m.ys[nd - 1] = m.rs[nd - 1];
+    if (slide) {
+      m.rs[nd - 2] = (a.rs[nd - 2] + 3) / 4 * 4;
+      m.rs[nd - 3] = (a.rs[nd - 3] + 1) / 2 * 2;
+      m.xs[nd - 2] = m.ys[nd - 2] = m.rs[nd - 2];
+      m.xs[nd - 3] = m.ys[nd - 3] = m.rs[nd - 3];
+    }
+    return m;
+  };
+  MulArgs best;
+  int kind = 0;
+  if (nd >= 4 && ctx.use_slide) {
+    MulArgs m = padded(true);
+    if (slide_mul_applicable(ctx, m) && args_macs(m) <= 1.7 * macs) { best = m; kind = 3; }
+  }
+  if (!kind) {
+    MulArgs m = padded(false);
+    if (blk_mul_applicable(ctx, m) && args_macs(m) <= 2.5 * macs) { best = m; kind = 2; }
+  }
+  if (kind) *out_best = best;
+  return kind;
+}
+static bool launch_mul_padded(Ctx& ctx, const MulArgs& a) {
+  const int nd = a.ndim;
+  MulArgs best;
+  const int kind = pad_plan(ctx, a, &best);
+  if (!kind) return false;
+  auto tail_elems = [&](const Shape& s) { u64 p = 1; for (int d = 1; d < nd; d++) p *= s[d]; return p; };
+  const u64 rows = a.rows.empty() ? a.row_count : a.rows.size();
+  if (prod(best.xs) >= (1ull << 32) - 4096 || prod(best.ys) >= (1ull << 32) - 4096 || rows * tail_elems(best.rs) >= (1ull << 32) - 4096) return false;
+  auto pad_operand = [&](const double* src, const Shape& from, const Shape& to) -> BufP {
+    if (from == to) return BufP();
+    BufP b = ctx.alloc(prod(to));
+    GTP_CUDA(cudaMemsetAsync(b->d, 0, prod(to) * sizeof(double), ctx.stream));
+    EwOperand A;
+    A.p = src;
+    A.shape = from;
+    launch_ew(ctx, EW_COPY, from, A, nullptr, b->d, to, {});
+    return b;
+  };
+  BufP xp = pad_operand(a.x, a.xs, best.xs), yp = pad_operand(a.y, a.ys, best.ys);
+  Shape zrows_p = best.rs, zrows = a.rs;
+  zrows_p[0] = rows;
+  zrows[0] = rows;
+  BufP zp = ctx.alloc(prod(zrows_p));
+  best.x = xp ? xp->d : a.x;
+  best.y = yp ? yp->d : a.y;
+  best.out = zp->d;
+  if (kind == 3) launch_mul_slide(ctx, best);
+  else launch_mul_blk(ctx, best);
+  EwOperand Z;   // crop: the leading box of the padded rows
+  Z.p = zp->d;
+  Z.shape = zrows_p;
+  launch_ew(ctx, EW_COPY, zrows, Z, nullptr, a.out, zrows, {});
+  return true;
+}
+
 void launch_mul(Ctx& ctx, const MulArgs& a_in) {
   MulArgs a = a_in;
   if (!a.rows.empty()) {
@@ -478,6 +572,7 @@ void launch_mul(Ctx& ctx, const MulArgs& a_in) {
   }
   if (ctx.fast_mul && ctx.use_stencil && launch_mul_stencil(ctx, a)) return;   // bit-exact, HBM-bound small-operand products
   if (ctx.fast_mul && ctx.use_axis && launch_mul_axis(ctx, a)) return;         // bit-exact, 1-d operand x N-d tensor
+  if (ctx.fast_mul && launch_mul_padded(ctx, a)) return;                       // odd extents: zero-extend, DFMA kernels, crop
   if (a.rows.empty()) {
     launch_mul_ordered(ctx, a);
     return;

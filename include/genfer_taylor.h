@@ -74,7 +74,8 @@ uint64_t gtp_ctx_launch_count(gtp_ctx* ctx);
  * +128 mul_linear as the reference's composition instead of the one-pass kernel, +256 small-operand stencil kernel off,
  * +512 stencil kernel with one instead of four coefficients per thread, +1024 device-resident N-D div / exp / log
  * recurrences off (host loops of product launches), +2048 fused Horner loop of subst_var off (three launches per step),
- * +4096 axis-convolution kernel (1-d operand x N-d tensor) off.
+ * +4096 axis-convolution kernel (1-d operand x N-d tensor) off, +8192 zero-extension of odd-shaped dense products to the DFMA
+ * kernels' extents off.
  * Environment (read at gtp_ctx_create): GTP_LAUNCH_HIST=1 prints per-kernel launch counts and host-time shares when the
  * context is destroyed; GTP_NO_SCALAR_POOL=1 / GTP_NO_FUSED_CLS=1 switch the host-written scalar slots / the fused
  * classification off. */
@@ -164,8 +165,9 @@ int gtp_mul_rowlist_raw(gtp_ctx* ctx, int ndim, const uint64_t* xshape, const do
                         const uint64_t* rows, uint64_t n_rows, double* out_rows);
 /* MAC count of the general product (trip counts of :975-977 and :1002-1004); FLOPs = 2*MACs. */
 double gtp_mul_macs(int ndim, const uint64_t* xshape, const uint64_t* yshape, const uint64_t* rshape);
-/* Which kernel gtp_mul_rows_raw would pick for these shapes: 0 reference-order (or the small-operand stencil kernel),
- * 2 2x2-blocked DFMA kernel, 3 sliding 1x2 DFMA kernel (dense cube slabs). */
+/* Which kernel gtp_mul_rows_raw would pick for these shapes: 0 the bit-exact reference-order family (reference-order kernel,
+ * small-operand stencil kernel, axis-convolution kernel), 2 2x2-blocked DFMA kernel, 3 sliding 1x2 DFMA kernel (dense cube
+ * slabs), 6 / 7 the blocked / sliding kernel after zero-extending odd extents (27, 31, 17 ...) to supported ones. */
 int gtp_mul_kernel_kind(gtp_ctx* ctx, int ndim, const uint64_t* xshape, const uint64_t* yshape,
                         const uint64_t* rshape);
 /* FP64 pipe microbenchmarks (the roofline denominator): runs `iters` dependent-chain DFMA (kind 0)

@@ -152,6 +152,26 @@ def test_axis_convolution_kernel_is_bit_exact(ctx, xs, ys, rs):
     assert np.array_equal(got.view(np.uint64), ref.view(np.uint64))
 
 
+ODD_SHAPES = [((27,) * 3,) * 3, ((13,) * 4,) * 3, ((17,) * 4,) * 3, ((31,) * 3,) * 3, ((9,) * 5,) * 3,
+              ((13, 17, 19, 21), (11, 17, 15, 21), (13, 17, 19, 21)), ((5, 27, 27, 27), (3, 20, 27, 25), (7, 27, 27, 27))]
+
+
+@pytest.mark.parametrize("xs,ys,rs", ODD_SHAPES)
+def test_odd_shaped_products_leave_the_reference_order_kernel(ctx, xs, ys, rs):
+    """Cube edges 27, 31, 17 ... (limit + 1 + sum of orders): zero-extended to the DFMA kernels' extents and cropped --
+    1e-12 against the oracle (all-positive inputs), and no longer on the ~0.15 TFLOP/s reference-order kernel."""
+    from oracle import oracle as O
+    from helpers import synth_uniform
+    x, y = synth_uniform(xs, 101), synth_uniform(ys, 202)
+    assert ctx.mul_kernel_kind(xs, ys, rs) in (2, 3, 6, 7)
+    ref = O.mul_raw(x, y, rs)
+    got = gpu_mul_raw(ctx, x, y, rs, fast=True)
+    assert rel_err(got, ref) <= RTOL, rel_err(got, ref)
+    rows = (1, 2, (rs[0] - 1) // 2)                       # a cyclic row shard goes through the same plan
+    got_rows = gpu_mul_raw(ctx, x, y, rs, rows=rows, fast=True)
+    assert rel_err(got_rows, ref[rows[0]::rows[1]][:rows[2]]) <= RTOL
+
+
 @pytest.mark.parametrize("n,d", [(4, 12), (4, 16), (5, 12), (5, 16), (4, 8), (4, 24), (4, 10)])
 def test_kernel_selection(ctx, n, d):
     """Dense cube slabs take the sliding kernel (3): whole slabs when they give >= 16 folded lanes and fit in shared
