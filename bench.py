@@ -337,7 +337,14 @@ def run_ours(args):
 
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
-    ctx = genfer_b200.Context(local, stream=stream.cuda_stream)
+    if world > 1:
+        # group context: the partitioning, the NCCL all-gather and the row-sharded result live INSIDE the library, behind
+        # the same gtp_mul a single-GPU caller uses (torch.distributed only ships the 128-byte NCCL id)
+        ids = [genfer_b200.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx = genfer_b200.Context.create_group(local, rank, world, ids[0], stream=stream.cuda_stream)
+    else:
+        ctx = genfer_b200.Context(local, stream=stream.cuda_stream)
     kind = ctx.mul_kernel_kind(shape, shape, shape)
 
     xh_np, yh_np = synth_inputs(n, d)
@@ -350,6 +357,9 @@ def run_ours(args):
     lo, hi, block = shard_bounds(d, world, rank)
     hy_shard = torch.zeros((block,) + shape[1:], dtype=torch.float64).pin_memory()
     hy_shard[: hi - lo] = hy[lo:hi]
+    hx_shard = torch.zeros((block,) + shape[1:], dtype=torch.float64).pin_memory()
+    hx_shard[: hi - lo] = hx[lo:hi]
+    TXd = genfer_b200.TaylorPoly.from_device(dx.data_ptr(), shape, shape, ctx)   # X resident and replicated
     out_rows = torch.empty((len(pp.rows),) + shape[1:], dtype=torch.float64, device="cuda")
     h_out = torch.empty((len(pp.rows),) + shape[1:], dtype=torch.float64).pin_memory()
     row_kernel = gpu_row_kernel(ctx)
@@ -362,12 +372,23 @@ def run_ours(args):
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
 
     def step(i=None):
-        y_full = pp.gather_operand(y_shard, d)            # NCCL all-gather (no-op at N=1)
+        if world == 1:
+            if i is not None:
+                kev[i][0].record()
+            row_kernel(shape, dx, shape, dy, shape, pp.rows, out_rows)
+            if i is not None:
+                kev[i][1].record()
+            return None
+        # N > 1: Y lives block-sharded; gtp_mul replicates it (ncclAllGather over NVLink, inside the library), computes
+        # this rank's folded-cyclic rows and leaves the result row-sharded
+        TY = genfer_b200.TaylorPoly.from_device_block(y_shard.data_ptr(), shape, shape, ctx)
+        TY.replicate()
         if i is not None:
             kev[i][0].record()
-        row_kernel(shape, dx, shape, y_full, shape, pp.rows, out_rows)
+        Z = TXd * TY
         if i is not None:
             kev[i][1].record()
+        return Z
 
     # ---- device-resident timing ------------------------------------------------------------
     torch.cuda.synchronize()
@@ -412,12 +433,11 @@ def run_ours(args):
             Y = genfer_b200.TaylorPoly.from_host_ptr(hy.data_ptr(), shape, shape, ctx)
             Z = X * Y
             Z.to_host_ptr(h_out.data_ptr())               # synchronises
-        else:
-            dx.copy_(hx, non_blocking=True)
-            y_shard.copy_(hy_shard, non_blocking=True)
-            step()
-            h_out.copy_(out_rows, non_blocking=True)
-            torch.cuda.synchronize()
+        else:             # the same operator surface on a group context: block-sharded uploads (1/N of the H2D traffic
+            X = genfer_b200.TaylorPoly.from_host_block_ptr(hx_shard.data_ptr(), shape, shape, ctx)   # per rank), NVLink
+            Y = genfer_b200.TaylorPoly.from_host_block_ptr(hy_shard.data_ptr(), shape, shape, ctx)   # all-gathers,
+            Z = X * Y                                                                                   # partitioned product,
+            Z.to_host_local_ptr(h_out.data_ptr())                                                       # D2H of this rank's rows
 
     for _ in range(min(W, 2)):
         e2e_step()
@@ -432,7 +452,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = flops * K / float(te[0]) / 1e9
-    h2d = hx.numel() * 8 + (hy.numel() * 8 if world == 1 else hy_shard.numel() * 8)
+    h2d = (hx.numel() + hy.numel()) * 8 if world == 1 else (hx_shard.numel() + hy_shard.numel()) * 8
     d2h = h_out.numel() * 8
     e2e_out_sample = h_out[0, :].clone() if rank == 0 else None   # Z[0, ...] (row 0 belongs to rank 0)
 
@@ -524,12 +544,13 @@ def run_ours(args):
                                      f"{3 * d ** n * 8 / 2 ** 20:.0f} MiB" + (" > 126 MB L2 (inputs larger than L2)" if 3 * d ** n * 8 > 126e6 else
                                                                                " (fits L2; compute-bound kernel, arithmetic intensity > 1 kFLOP/B)"),
                            "parallelism": "1 GPU" if world == 1 else
-                           f"output rows folded-cyclic over {world} GPUs, Y block-sharded + NCCL all-gather per step",
+                           f"output rows folded-cyclic over {world} GPUs inside gtp_mul (group context), Y block-sharded + in-library NCCL all-gather per step",
                            "kernel": roofline["kernel"]},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "api": "gtp_from_host x2 -> gtp_mul -> gtp_to_host" if world == 1 else
-                               "pinned H2D (X, Y shard) -> all-gather -> gtp_mul_rowlist_raw -> D2H of the rank's rows"},
+                               "gtp_from_host_block x2 (X, Y block shards) -> gtp_mul on a group context (in-library ncclAllGather x2, "
+                               "partitioned rows) -> gtp_to_host_local (this rank's rows)"},
                 "gpu_launches": int(launches),
                 "roofline": roofline, "aux_rooflines": aux, "cpu_baseline": cpu, "parity": parity,
                 "kernel_ms_max_over_ranks": ms_kernel_max,

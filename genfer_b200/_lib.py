@@ -32,6 +32,18 @@ _SIGS = {
     "gtp_ctx_stream": (vp, [vp]),
     "gtp_ctx_launch_count": (C.c_uint64, [vp]),
     "gtp_ctx_set_fast_mul": (C.c_int, [vp, C.c_int]),
+    "gtp_nccl_unique_id": (C.c_int, [vp]),
+    "gtp_ctx_create_group": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, vp, vpp]),
+    "gtp_ctx_group_info": (C.c_int, [vp, intp, intp, u64p, u64p]),
+    "gtp_ctx_set_partition_threshold": (C.c_int, [vp, C.c_uint64]),
+    "gtp_partition_rows": (C.c_uint64, [C.c_uint64, C.c_int, C.c_int, u64p]),
+    "gtp_partition_block": (None, [C.c_uint64, C.c_int, C.c_int, u64p, u64p, u64p]),
+    "gtp_from_host_block": (C.c_int, [vp, C.c_int, u64p, u64p, vp, vpp]),
+    "gtp_from_device_block": (C.c_int, [vp, C.c_int, u64p, u64p, vp, vpp]),
+    "gtp_is_distributed": (C.c_int, [vp]),
+    "gtp_replicate": (C.c_int, [vp, vp]),
+    "gtp_local_rows": (C.c_uint64, [vp, u64p]),
+    "gtp_to_host_local": (C.c_int, [vp, vp, vp]),
     "gtp_from_host": (C.c_int, [vp, C.c_int, u64p, u64p, f64p, vpp]),
     "gtp_from_device": (C.c_int, [vp, C.c_int, u64p, u64p, vp, vpp]),
     "gtp_to_host": (C.c_int, [vp, vp, vp]),

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgenfer_taylor.so")
-SOURCES = ["api.cu", "api_uni.cu", "eval_api.cpp", "kernels_elem.cu", "kernels_mul.cu", "kernels_mul_blk.cu", "kernels_mul_slide.cu", "kernels_mul_axis.cu", "kernels_rec.cu", "kernels_wave.cu", "kernels_horner.cu",
+SOURCES = ["api.cu", "api_uni.cu", "group.cu", "eval_api.cpp", "kernels_elem.cu", "kernels_mul.cu", "kernels_mul_blk.cu", "kernels_mul_slide.cu", "kernels_mul_axis.cu", "kernels_rec.cu", "kernels_wave.cu", "kernels_horner.cu",
            "univariate.cu"]
 HEADERS = ["common.hpp", "kernels.cuh", "device_sync.cuh", os.path.join("..", "..", "include", "genfer_taylor.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -55,7 +55,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if failed:
         raise RuntimeError("nvcc failed")
     if procs or force or _stale(LIB, objs):
-        cmd = [nvcc(), "-shared", "--cudart=static", "-o", LIB, *objs, "-lpthread", "-ldl", "-lrt"]
+        cmd = [nvcc(), "-shared", "--cudart=static", "-o", LIB, *objs, "-lpthread", "-ldl", "-lrt"]   # NCCL is dlopen'ed (group.cu), never linked
         subprocess.run(cmd, check=True)
     return LIB
 

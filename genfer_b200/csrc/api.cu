@@ -102,6 +102,12 @@ PolyP make_poly(BufP buf, u64 off, Shape shape, Shape degrees) {
   p->degrees = std::move(degrees);
   return p;
 }
+// the buffer behind a handle (replicates a distributed tensor first)
+BufP buf_of(const gtp_poly& a) {
+  if (!a.shard) return a.buf;
+  replicate(*a.shard);
+  return a.shard->full;
+}
 PolyP share(const gtp_poly& a) {  // Clone: buffers are immutable, so sharing is a deep copy in effect
   PolyP p(new gtp_poly(a));
   return p;
@@ -269,7 +275,7 @@ PolyP truncate_degrees(Ctx& c, const gtp_poly& a, const Shape& d) {
     return r;
   }
   if (!cut_inner) {  // only the leading axis shrinks: the result is a prefix of the same buffer
-    PolyP r = make_poly(a.buf, a.off, ns, nd);
+    PolyP r = make_poly(buf_of(a), a.off, ns, nd);
     return r;
   }
   return copy_box(c, a, Shape(ns.size(), 0), ns, nd);
@@ -301,6 +307,9 @@ PolyP ew_scalar(Ctx& c, EwOp op, const gtp_poly& a, const gtp_poly& sp, const Sh
   return r;
 }
 
+}  // namespace
+namespace gtp { void partition_rows(u64 n_rows, int world, int rank, std::vector<u64>* out); }   // group.cu
+namespace {
 PolyP poly_add(Ctx& c, const gtp_poly& a0, const gtp_poly& b0, bool subtract);
 PolyP poly_mul(Ctx& c, const gtp_poly& a0, const gtp_poly& b0);
 PolyP poly_div(Ctx& c, const gtp_poly& a0, const gtp_poly& b0, PolyP* recip_cache = nullptr);
@@ -404,6 +413,34 @@ PolyP poly_mul(Ctx& c, const gtp_poly& a0, const gtp_poly& b0) {
     return mul_linear(c, *at, bt->cls->c, bt->cls->m, bt->ptr() + stride_of(bt->shape, v), v, s, d);
   }
   // general case (:1064-1070)
+  // (threshold 0 partitions every general product, also on a one-rank group: single-GPU tests of this path)
+  if (c.group && (c.group->world > 1 || c.group->threshold == 0) && shape.size() >= 2 && prod(shape) >= c.group->threshold &&
+      shape[0] >= 2 * (u64)c.group->world) {
+    // Partitioned product: this rank computes its folded-cyclic leading-axis rows; the result stays
+    // row-sharded until somebody needs all of it.  Both operands are read whole (replicated on first use).
+    auto sh = std::make_shared<ShardState>();
+    sh->kind = ShardState::ROWS;
+    sh->ctx = &c;
+    sh->group = c.group;
+    partition_rows(shape[0], c.group->world, c.group->rank, &sh->rows);
+    sh->n_rows = shape[0];
+    sh->row_elems = prod(shape) / shape[0];
+    sh->local = c.alloc(std::max<u64>(sh->rows.size() * sh->row_elems, 1));
+    MulArgs m;
+    m.ndim = (int)shape.size();
+    m.xs = at->shape;
+    m.ys = bt->shape;
+    m.rs = shape;
+    m.x = at->ptr();
+    m.y = bt->ptr();
+    m.out = sh->local->d;
+    m.rows = sh->rows;
+    if (!m.rows.empty()) launch_mul(c, m);
+    c.group->partitioned_products++;
+    PolyP r = make_poly(nullptr, 0, shape, d);
+    r->shard = sh;
+    return r;
+  }
   PolyP r = new_uninit(c, shape, d);
   MulArgs m;
   m.ndim = (int)shape.size();
@@ -1179,7 +1216,7 @@ int gtp_remove_last_variable(gtp_ctx* c, const gtp_poly* a, gtp_poly** out) {  /
     Shape d(a->degrees.begin(), a->degrees.end() - 1);
     Shape s(a->shape.begin(), a->shape.end() - 1);
     if (a->shape[v] == 1) {
-      *out = make_poly(a->buf, a->off, s, d).release();
+      *out = make_poly(buf_of(*a), a->off, s, d).release();
       return;
     }
     Shape ext = a->shape;

@@ -184,8 +184,22 @@ struct FusedCls {
   Shape shape;
 };
 
+// ---- multi-GPU group: one context = one stream + one NCCL communicator --------------------------------
+// NCCL is loaded with dlopen when a group context is created (group.cu): the library has no link-time dependency on it
+// and single-GPU use never touches it.
+struct NcclApi;
+struct Group {
+  int rank = 0, world = 1;
+  void* comm = nullptr;                 // ncclComm_t
+  std::shared_ptr<NcclApi> api;
+  u64 threshold = 10000000;             // products with at least this many output coefficients are partitioned (north_star)
+  u64 partitioned_products = 0, gathers = 0;   // statistics (bench / tests)
+  ~Group();
+};
+
 struct Ctx {
   int device = 0;
+  std::shared_ptr<Group> group;        // null: single-GPU context
   std::shared_ptr<StreamCore> core;
   cudaStream_t stream = nullptr;  // == core->stream
   int sm_count = 148;
@@ -239,6 +253,24 @@ struct ClassInfo {
 
 }  // namespace gtp
 
+namespace gtp {
+// A polynomial whose coefficients are distributed over the ranks of a group context: either the folded-cyclic leading-axis
+// ROWS a partitioned product left on this rank, or this rank's contiguous BLOCK of leading-axis slices (an operand
+// uploaded in shards).  `shape` of the handle is always the FULL shape.  The first consumer that needs the whole tensor
+// replicates it (NCCL broadcasts / all-gather on the context's stream) and caches the result here, shared by all clones.
+struct ShardState {
+  enum Kind { ROWS, BLOCK } kind = ROWS;
+  Ctx* ctx = nullptr;
+  std::shared_ptr<Group> group;
+  BufP local;                    // ROWS: rows[i] at local + i * row_elems;  BLOCK: the (zero-padded) block of `block` slices
+  const double* local_ptr = nullptr;   // BLOCK built over caller-owned device memory (gtp_from_device_block)
+  std::vector<u64> rows;         // ROWS: this rank's leading-axis rows, ascending
+  u64 n_rows = 0, row_elems = 0, block = 0;
+  BufP full;                     // set once replicated
+};
+const double* replicate(const ShardState& s);   // group.cu; idempotent
+}  // namespace gtp
+
 // The opaque handle types of the C ABI
 struct gtp_poly {
   gtp::BufP buf;
@@ -246,7 +278,8 @@ struct gtp_poly {
   gtp::Shape shape;    // coeffs.shape()
   gtp::Shape degrees;  // degrees_p1
   std::shared_ptr<gtp::ClassInfo> cls = std::make_shared<gtp::ClassInfo>();  // shared by O(1) clones of the same data
-  const double* ptr() const { return buf->d + off; }
+  std::shared_ptr<gtp::ShardState> shard;   // set: distributed over a group context (buf is null until replicated)
+  const double* ptr() const { return shard ? gtp::replicate(*shard) + off : buf->d + off; }
   gtp::u64 len() const { return gtp::prod(shape); }
   int ndim() const { return (int)shape.size(); }
 };

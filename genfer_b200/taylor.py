@@ -44,6 +44,32 @@ class Context:
         self.h = h
         self.device = device
 
+    @classmethod
+    def create_group(cls, device: int, rank: int, world: int, unique_id: bytes, stream: Optional[int] = None) -> "Context":
+        """Group context (gtp_ctx_create_group): one NCCL communicator on the context's stream.  `unique_id` are the 128
+        bytes of :func:`nccl_unique_id` from rank 0, shipped to every rank by the caller (bench.py: torch.distributed)."""
+        self = cls.__new__(cls)
+        self.lib = _lib.load()
+        assert len(unique_id) == 128
+        h = C.c_void_p()
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        rc = self.lib.gtp_ctx_create_group(device, C.c_void_p(stream) if stream else None, rank, world, buf, C.byref(h))
+        if rc != 0:
+            raise TaylorError(rc, "gtp_ctx_create_group failed (no CUDA device / NCCL?)")
+        self.h = h
+        self.device = device
+        return self
+
+    def group_info(self):
+        """(rank, world, partitioned products so far, replications so far)"""
+        r, w = C.c_int(), C.c_int()
+        pp, g = C.c_uint64(), C.c_uint64()
+        self.check(self.lib.gtp_ctx_group_info(self.h, C.byref(r), C.byref(w), C.byref(pp), C.byref(g)))
+        return r.value, w.value, int(pp.value), int(g.value)
+
+    def set_partition_threshold(self, coefficients: int):
+        self.check(self.lib.gtp_ctx_set_partition_threshold(self.h, int(coefficients)))
+
     def close(self):
         if getattr(self, "h", None):
             self.lib.gtp_ctx_destroy(self.h)
@@ -88,6 +114,27 @@ class Context:
 
     def mul_kernel_kind(self, xshape, yshape, rshape) -> int:
         return int(self.lib.gtp_mul_kernel_kind(self.h, len(rshape), _u64(xshape), _u64(yshape), _u64(rshape)))
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    rc = _lib.load().gtp_nccl_unique_id(buf)
+    if rc != 0:
+        raise TaylorError(rc, "gtp_nccl_unique_id failed (NCCL not loadable?)")
+    return buf.raw
+
+
+def partition_rows(n_rows: int, world: int, rank: int):
+    """Folded-cyclic leading-axis rows of `rank` (gtp_partition_rows; integer work, no device needed)."""
+    out = (C.c_uint64 * max(n_rows, 1))()
+    n = int(_lib.load().gtp_partition_rows(n_rows, world, rank, out))
+    return [int(out[i]) for i in range(n)]
+
+
+def partition_block(n_slices: int, world: int, rank: int):
+    lo, hi, b = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    _lib.load().gtp_partition_block(n_slices, world, rank, C.byref(lo), C.byref(hi), C.byref(b))
+    return int(lo.value), int(hi.value), int(b.value)
 
 
 def mul_macs(xshape, yshape, rshape) -> float:
@@ -151,6 +198,32 @@ class TaylorPoly:
         ctx = ctx or default_context()
         return cls._make(ctx, "gtp_from_host", len(shape), _u64(shape), _u64(degrees_p1),
                          C.cast(C.c_void_p(ptr), _lib.f64p))
+
+    @classmethod
+    def from_host_block_ptr(cls, ptr: int, shape: Sequence[int], degrees_p1: Sequence[int], ctx: Context) -> "TaylorPoly":
+        """Block-sharded upload (gtp_from_host_block): `ptr` holds this rank's leading-axis slices of the FULL `shape`."""
+        return cls._make(ctx, "gtp_from_host_block", len(shape), _u64(shape), _u64(degrees_p1), C.c_void_p(ptr))
+
+    @classmethod
+    def from_device_block(cls, ptr: int, shape: Sequence[int], degrees_p1: Sequence[int], ctx: Context) -> "TaylorPoly":
+        return cls._make(ctx, "gtp_from_device_block", len(shape), _u64(shape), _u64(degrees_p1), C.c_void_p(ptr))
+
+    def is_distributed(self) -> bool:
+        return bool(self.ctx.lib.gtp_is_distributed(self._h))
+
+    def replicate(self) -> "TaylorPoly":
+        self.ctx.check(self.ctx.lib.gtp_replicate(self.ctx.h, self._h))
+        return self
+
+    def local_rows(self):
+        n0 = self.array_shape()[0] if self.num_vars() else 1
+        out = (C.c_uint64 * max(n0, 1))()
+        n = int(self.ctx.lib.gtp_local_rows(self._h, out))
+        return [int(out[i]) for i in range(n)]
+
+    def to_host_local_ptr(self, ptr: int) -> None:
+        """D2H of this rank's rows of a row-sharded result (no collective; synchronises)."""
+        self.ctx.check(self.ctx.lib.gtp_to_host_local(self.ctx.h, self._h, C.c_void_p(ptr)))
 
     def to_host_ptr(self, ptr: int) -> None:
         """Copy the stored coefficients to a host address (synchronises)."""

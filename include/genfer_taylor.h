@@ -81,6 +81,30 @@ uint64_t gtp_ctx_launch_count(gtp_ctx* ctx);
  * classification off. */
 int gtp_ctx_set_fast_mul(gtp_ctx* ctx, int enabled);
 
+/* ---- multi-GPU groups (one process per GPU, SPMD) --------------------------------- */
+/* Every rank makes the same sequence of calls on replicated handles.  A group context owns one NCCL communicator on its
+ * stream (NCCL is dlopen'ed: libnccl.so.2).  gtp_mul partitions a general product (:984-1012) whose result has at least
+ * `threshold` coefficients (default 10^7, north_star) over the ranks by folded-cyclic leading-axis rows -- row k0 costs
+ * k0 + 1 sub-products (:1001-1010), rank r owns k0 mod 2W in {r, 2W-1-r} -- and leaves the result ROW-SHARDED; the next
+ * consumer that needs the whole tensor (the next product of a Horner chain :574-578, gtp_to_host, ...) replicates it with
+ * one grouped NCCL broadcast per row, cached in the handle.  Everything else runs replicated. */
+int gtp_nccl_unique_id(void* out128);                       /* rank 0 calls this and ships the 128 bytes to the others */
+int gtp_ctx_create_group(int device, void* cuda_stream, int rank, int world, const void* id128, gtp_ctx** out);
+int gtp_ctx_group_info(gtp_ctx* ctx, int* rank, int* world, uint64_t* partitioned_products, uint64_t* gathers);
+int gtp_ctx_set_partition_threshold(gtp_ctx* ctx, uint64_t coefficients);   /* 0: partition every general product (tests) */
+/* the row map and the block map as plain integer functions (no device needed) */
+uint64_t gtp_partition_rows(uint64_t n_rows, int world, int rank, uint64_t* rows_out);
+void gtp_partition_block(uint64_t n_slices, int world, int rank, uint64_t* lo, uint64_t* hi, uint64_t* block);
+/* An operand uploaded in shards: `block_data` holds this rank's leading-axis slices [lo, hi) of the tensor of FULL shape
+ * `shape` (gtp_partition_block); 1/W of the host-to-device traffic per rank, replicated over NVLink by one ncclAllGather
+ * when first used.  gtp_from_device_block wraps a zero-padded device block of `block` slices without copying. */
+int gtp_from_host_block(gtp_ctx* ctx, int ndim, const uint64_t* shape, const uint64_t* degrees_p1, const double* block_data, gtp_poly** out);
+int gtp_from_device_block(gtp_ctx* ctx, int ndim, const uint64_t* shape, const uint64_t* degrees_p1, const double* device_block, gtp_poly** out);
+int gtp_is_distributed(const gtp_poly* p);                  /* 1: sharded and not replicated yet */
+int gtp_replicate(gtp_ctx* ctx, const gtp_poly* p);         /* collective; idempotent */
+uint64_t gtp_local_rows(const gtp_poly* p, uint64_t* rows_out);   /* rows of a row-sharded result held by this rank */
+int gtp_to_host_local(gtp_ctx* ctx, const gtp_poly* p, double* out); /* D2H of those rows only (no collective); synchronises */
+
 /* ---- construction, transfer, metadata ------------------------------------------------------- */
 /* TaylorPoly::new (:33-41): upload `data` (row-major over `shape`, prod(shape) doubles).  `data` may be reused or freed
  * as soon as the call returns: pageable memory is staged by the driver, and for a pinned / registered source (whose DMA

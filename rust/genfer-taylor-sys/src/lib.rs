@@ -23,6 +23,18 @@ extern "C" {
     pub fn gtp_ctx_stream(ctx: *mut gtp_ctx) -> *mut c_void;
     pub fn gtp_ctx_launch_count(ctx: *mut gtp_ctx) -> u64;
     pub fn gtp_ctx_set_fast_mul(ctx: *mut gtp_ctx, enabled: c_int) -> c_int;
+    pub fn gtp_nccl_unique_id(out128: *mut c_void) -> c_int;
+    pub fn gtp_ctx_create_group(device: c_int, cuda_stream: *mut c_void, rank: c_int, world: c_int, id128: *const c_void, out: *mut *mut gtp_ctx) -> c_int;
+    pub fn gtp_ctx_group_info(ctx: *mut gtp_ctx, rank: *mut c_int, world: *mut c_int, partitioned_products: *mut u64, gathers: *mut u64) -> c_int;
+    pub fn gtp_ctx_set_partition_threshold(ctx: *mut gtp_ctx, coefficients: u64) -> c_int;
+    pub fn gtp_partition_rows(n_rows: u64, world: c_int, rank: c_int, rows_out: *mut u64) -> u64;
+    pub fn gtp_partition_block(n_slices: u64, world: c_int, rank: c_int, lo: *mut u64, hi: *mut u64, block: *mut u64);
+    pub fn gtp_from_host_block(ctx: *mut gtp_ctx, ndim: c_int, shape: *const u64, degrees_p1: *const u64, block_data: *const f64, out: *mut *mut gtp_poly) -> c_int;
+    pub fn gtp_from_device_block(ctx: *mut gtp_ctx, ndim: c_int, shape: *const u64, degrees_p1: *const u64, device_block: *const f64, out: *mut *mut gtp_poly) -> c_int;
+    pub fn gtp_is_distributed(p: *const gtp_poly) -> c_int;
+    pub fn gtp_replicate(ctx: *mut gtp_ctx, p: *const gtp_poly) -> c_int;
+    pub fn gtp_local_rows(p: *const gtp_poly, rows_out: *mut u64) -> u64;
+    pub fn gtp_to_host_local(ctx: *mut gtp_ctx, p: *const gtp_poly, out: *mut f64) -> c_int;
     pub fn gtp_from_host(ctx: *mut gtp_ctx, ndim: c_int, shape: *const u64, degrees_p1: *const u64, data: *const f64, out: *mut *mut gtp_poly) -> c_int;
     pub fn gtp_from_device(ctx: *mut gtp_ctx, ndim: c_int, shape: *const u64, degrees_p1: *const u64, device_data: *const f64, out: *mut *mut gtp_poly) -> c_int;
     pub fn gtp_to_host(ctx: *mut gtp_ctx, p: *const gtp_poly, out: *mut f64) -> c_int;
