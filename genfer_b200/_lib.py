@@ -134,6 +134,19 @@ def load() -> C.CDLL:
             raise ImportError(
                 f"{LIB_PATH} is missing: build it with `python genfer_b200/build.py` "
                 "(there is no CPU fallback for the f64 Taylor path)")
+        if "GTP_NCCL_LIB" not in os.environ:
+            # group contexts dlopen NCCL: in a Python process it must be the copy PyTorch is linked against (same soname,
+            # the loader would otherwise hand torch the system's older libnccl.so.2 -- or us torch's, depending on order)
+            try:
+                import importlib.util
+                spec = importlib.util.find_spec("nvidia.nccl")
+                for base in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+                    cand = os.path.join(base, "lib", "libnccl.so.2")
+                    if os.path.exists(cand):
+                        os.environ["GTP_NCCL_LIB"] = cand
+                        break
+            except Exception:
+                pass
         lib = C.CDLL(LIB_PATH)
         for name, (restype, argtypes) in _SIGS.items():
             fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol

@@ -35,8 +35,12 @@ static std::shared_ptr<NcclApi> load_nccl() {
   static std::shared_ptr<NcclApi> cached;
   if (cached) return cached;
   auto api = std::make_shared<NcclApi>();
-  for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
-    api->lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+  // GTP_NCCL_LIB names the library to use.  A process that also hosts PyTorch must load the SAME libnccl.so.2 torch
+  // links against (its bundled copy): the loader keys shared objects by soname, so whichever copy comes first serves both
+  // (genfer_b200/_lib.py points GTP_NCCL_LIB at torch's copy).  Other hosts get the system's NCCL.
+  const char* env = getenv("GTP_NCCL_LIB");
+  for (const char* name : {env ? env : "libnccl.so.2", "libnccl.so.2", "libnccl.so"}) {
+    api->lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
     if (api->lib) break;
   }
   GTP_CHECK(api->lib, GTP_ERR_CUDA, std::string("cannot load NCCL (libnccl.so.2): ") + (dlerror() ? dlerror() : "not found"));
