@@ -982,6 +982,7 @@ int gtp_ctx_create(int device, void* cuda_stream, gtp_ctx** out) {
     delete c;
     return rc;
   }
+  if (const char* fm = getenv("GTP_FAST_MUL")) gtp_ctx_set_fast_mul(c, atoi(fm));   // A/B measurements of whole programs
   *out = c;
   return GTP_OK;
 }
@@ -1025,6 +1026,8 @@ int gtp_ctx_set_fast_mul(gtp_ctx* c, int enabled) {
   c->use_horner = (enabled & 2048) == 0;
   c->use_axis = (enabled & 4096) == 0;
   c->use_pad = (enabled & 8192) == 0;
+  c->use_bulk = (enabled & 16384) == 0;
+  c->bulk_products = (enabled & 32768) != 0;
   c->stencil_v4 = (enabled & 512) == 0;
   c->slide_tile = ((enabled >> 5) & 3) == 1 ? 4 : (((enabled >> 5) & 3) == 2 ? 8 : 0);   // A/B measurements
   enabled &= 3;

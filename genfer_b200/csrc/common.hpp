@@ -217,6 +217,8 @@ struct Ctx {
   std::shared_ptr<void> blk_plans;   // per-context cache of product plans (kernels_mul_blk.cu)
   std::shared_ptr<void> slide_plans; // same for kernels_mul_slide.cu
   std::shared_ptr<void> wave_tables; // level tables of the device-resident recurrences (kernels_wave.cu)
+  bool bulk_products = false;        // also run plain small-operand products on the row-staged kernel (A/B; slower than the gather kernel)
+  bool use_bulk = true;              // row-staged (bulk-copy / TMA) variant of the Horner step and the small-operand product (A/B tests)
   bool use_pad = true;               // zero-extend odd-shaped dense products to the DFMA kernels' extents (A/B tests)
   bool use_axis = true;              // 1-d operand x N-d tensor: batched axis convolution kernel (false: reference-order kernel; A/B tests)
   bool use_horner = true;            // fused Horner loop of subst_var for substitutions of <= 32 coefficients (A/B tests)

@@ -149,6 +149,350 @@ __global__ void __launch_bounds__(HN_T) k_horner(const __grid_constant__ HornerP
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Row-staged variant for HBM-sized tensors (rows of 16..1024 coefficients along the last effective axis): the TMA engine
+// streams whole source rows into shared memory with bulk asynchronous copies (cp.async.bulk + mbarrier complete_tx; SASS
+// UBLKCP), two stages deep, while the CTA multiplies the previous batch out of shared memory.  One-thread-per-coefficient
+// gathers (k_horner above, k_mul_stencil_v4) are latency-bound on these tensors: 45 % of HBM with 0.64 eligible warps per
+// cycle (profiles/r01k_stencil_ncu.json); here address generation is per ROW (one elected thread), loads are 2-KB bulk
+// transfers and the arithmetic reads conflict-free shared memory.
+//   An output row (all effective axes but the last fixed) needs one source row per GROUP of terms (terms that share their
+// outer offsets); a batch is HB_R consecutive output rows.  Source rows start at arbitrary element offsets: the copy
+// starts at the 16-byte-aligned element below (shift 0 / 1) and the consumer indexes past the shift; the last-axis bounds
+// are predicates, absent source rows (outer index out of range) skip their group exactly like the gather kernels do --
+// per-coefficient arithmetic and its order are identical to k_horner's.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int HB_R = 8;          // output rows per batch
+constexpr int HB_MAXG = 16;      // groups
+constexpr int HB_T = 256;
+constexpr int HB_NS = 4;         // ring stages
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+struct HornerBulkP {
+  HornerP h;
+  int ng;                                   // groups
+  int ra;                                   // first axis of the row block: axes ra .. ne-1 form one contiguous block of the source
+  int R;                                    // blocks per batch
+  unsigned char gm[HB_MAXG][HN_MAXE];       // outer offsets of group g (axes < ra; zero on the block axes)
+  unsigned char g_first[HB_MAXG], g_count[HB_MAXG];   // terms of group g: [g_first, g_first + g_count)
+  unsigned slot;                            // doubles per staged block slot (even)
+  int add_mode;                             // 0: product only (plain stencil product), 1: Add general path, 2: Add scalar path
+};
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// warp 0: producer (address generation + bulk copies, lanes over the (block, group) pairs of a batch);
+// warps 1 .. 7: consumers.  full[st]: the producer's expect_tx arrival + the copies' bytes; empty[st]: one arrival per consumer.
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f64(unsigned addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
+
+// NT: compile-time bound on the number of terms (2, 4, 8, 16, 32): the term loop is fully unrolled, so the term offsets and
+// group flags are immediate constant-bank operands and the substitution's coefficients live in registers (as in k_mul_stencil).
+template <int NT>
+__global__ void __launch_bounds__(HB_T) k_horner_rows(const __grid_constant__ HornerBulkP bp) {
+  const HornerP& p = bp.h;
+  extern __shared__ __align__(16) double hb_sm[];
+  __shared__ __align__(8) unsigned long long s_full[HB_NS], s_empty[HB_NS];
+  __shared__ unsigned char s_shift[HB_NS][HB_R * HB_MAXG];   // 0 / 1: element shift of the staged block; 255: absent
+  __shared__ long long s_so[HB_NS][HB_R];                    // offset of the output block's slice coefficients in `self`
+  __shared__ unsigned char s_rowok[HB_NS][HB_R];             // bit 0: block inside the product, bit 1: inside the slice (axes < ra)
+  constexpr unsigned NCONS = HB_T - 32;
+  const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  double sv[NT];
+#pragma unroll
+  for (int t = 0; t < NT; t++) sv[t] = t < p.nt ? p.subst[p.sidx[t]] : 0.0;
+  const unsigned sm_base = smem_u32(hb_sm);
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < HB_NS; q++) {
+      mbar_init(&s_full[q], 1);
+      mbar_init(&s_empty[q], NCONS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int ne = p.ne, ng = bp.ng, ra = bp.ra, R = bp.R;
+  unsigned cur[HN_MAXE], nxt[HN_MAXE], prodsh[HN_MAXE];
+#pragma unroll
+  for (int a = 0; a < HN_MAXE; a++) cur[a] = a < ne ? p.shape0[a] : 1u;
+  unsigned phase = 0;
+  unsigned n_batches_done = 0;       // batches this CTA has pushed through the ring so far (same count on both sides)
+  const double* src = p.res0;
+  const unsigned stage_doubles = (unsigned)R * ng * bp.slot;
+  for (unsigned step = 0; step < p.nsteps; step++) {
+    double* dst = p.buf[step & 1u];
+    const unsigned i = p.i_top - step;
+    unsigned nsr = 1, QR = 1;          // super-rows (axes < ra) and rows per block (axes ra .. ne-2)
+    long long cstr[HN_MAXE];
+#pragma unroll
+    for (int a = 0; a < HN_MAXE; a++) {
+      if (a < ne) {
+        const unsigned long long s = (unsigned long long)cur[a] + p.sshape[a] - 1ull;
+        prodsh[a] = (unsigned)min(s, (unsigned long long)p.d[a]);
+        nxt[a] = bp.add_mode ? max(prodsh[a], p.slice[a]) : prodsh[a];
+        if (a < ra) nsr *= nxt[a];
+        else if (a < ne - 1) QR *= nxt[a];
+      } else {
+        prodsh[a] = nxt[a] = 1u;
+      }
+    }
+    {
+      long long st = 1;
+#pragma unroll
+      for (int a = HN_MAXE - 1; a >= 0; --a) {
+        if (a < ne) { cstr[a] = st; st *= (long long)cur[a]; } else cstr[a] = 0;
+      }
+    }
+    const unsigned L_src = cur[ne - 1], L_out = nxt[ne - 1], L_prod = prodsh[ne - 1];
+    const unsigned BS = QR * L_src, BO = QR * L_out;     // source / output elements of a block (rows per block equal: see host)
+    const double* slice_base = p.self + (long long)i * p.self_vstr;
+    const unsigned per_cta = (nsr + gridDim.x - 1) / gridDim.x;
+    const unsigned row_lo = min(nsr, blockIdx.x * per_cta), row_hi = min(nsr, row_lo + per_cta);
+    const unsigned nb = (row_hi - row_lo + R - 1) / R;
+
+    if (warp == 0) {
+      // ---------------- producer ----------------
+      if (lane == 0) asm volatile("fence.proxy.async;" ::: "memory");   // other CTAs' generic-proxy stores (previous step)
+      __syncwarp();
+      for (unsigned b = 0; b < nb; b++) {
+        const unsigned seq = n_batches_done + b, st = seq % HB_NS;
+        if (seq >= HB_NS) mbar_wait(&s_empty[st], ((seq / HB_NS) - 1u) & 1u);   // the consumers released this stage's previous use
+        double* base = hb_sm + (size_t)st * stage_doubles;
+        const unsigned r0 = row_lo + b * R;
+        unsigned bytes = 0;
+        for (unsigned pr = lane; pr < (unsigned)(R * ng); pr += 32u) {
+          const unsigned r = pr / ng, g = pr - r * ng;
+          unsigned char sh = 255;
+          if (r0 + r < row_hi) {
+            unsigned rem = r0 + r;
+            bool in_prod = true, in_slice = true, ok = true;
+            long long so = 0, off = 0;
+#pragma unroll
+            for (int a = HN_MAXE - 2; a >= 0; --a) {
+              if (a < ra) {
+                const unsigned q = rem / nxt[a], ka = rem - q * nxt[a];
+                rem = q;
+                in_prod = in_prod && ka < prodsh[a];
+                in_slice = in_slice && ka < p.slice[a];
+                so += (long long)ka * p.selfstr[a];
+                const unsigned idx = ka - (unsigned)bp.gm[g][a];
+                ok = ok && idx < cur[a];
+                off += (long long)idx * cstr[a];
+              }
+            }
+            if (g == 0) {
+              s_rowok[st][r] = (unsigned char)((in_prod ? 1 : 0) | (in_slice ? 2 : 0));
+              s_so[st][r] = so;
+            }
+            if (ok && in_prod) {
+              // copy [off - shift, off - shift + n): 16-byte aligned start, even length, never past the block's last element;
+              // an odd tail element travels by an ordinary load and store of this lane (ordered before its arrival below)
+              const unsigned shift = (unsigned)(off & 1ll);
+              const unsigned n = (shift + BS) & ~1u;
+              if (n) {
+                bulk_g2s(base + (size_t)pr * bp.slot, src + (off - shift), n * 8u, &s_full[st]);
+                bytes += n * 8u;
+              }
+              if (n < shift + BS) base[(size_t)pr * bp.slot + n] = ldcg(src + (off - shift) + n);
+              sh = (unsigned char)shift;
+            }
+          }
+          s_shift[st][pr] = sh;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) mbar_expect_tx(&s_full[st], bytes);   // release: the row tables and tail elements above are visible to whoever sees the phase
+      }
+    } else {
+      // ---------------- consumers: a warp takes whole rows (no per-coefficient index decode), lanes along the row ----------------
+      const unsigned cw = warp - 1u;
+      constexpr unsigned NCW = NCONS / 32u;
+      for (unsigned b = 0; b < nb; b++) {
+        const unsigned seq = n_batches_done + b, st = seq % HB_NS;
+        mbar_wait(&s_full[st], (seq / HB_NS) & 1u);
+        const double* base = hb_sm + (size_t)st * stage_doubles;
+        const unsigned r0 = row_lo + b * R;
+        const unsigned rows_here = min((unsigned)R, row_hi - r0);
+        for (unsigned rr = cw; rr < rows_here * QR; rr += NCW) {
+          const unsigned r = rr / QR, q = rr - r * QR;
+          const unsigned char rk = s_rowok[st][r];
+          const unsigned sr = r0 + r;
+          // slice row (Add general path): decode the block-axis indices of q once per row
+          bool b_row = (rk & 2) != 0;
+          long long so = s_so[st][r];
+          if (bp.add_mode == 1) {
+            unsigned rem = q;
+#pragma unroll
+            for (int a = HN_MAXE - 2; a >= 0; --a) {
+              if (a >= ra && a < ne - 1) {
+                const unsigned qq = rem / nxt[a], ka = rem - qq * nxt[a];
+                rem = qq;
+                b_row = b_row && ka < p.slice[a];
+                so += (long long)ka * p.selfstr[a];
+              }
+            }
+          }
+          const unsigned qoff = q * L_src;
+          double* drow = dst + (size_t)sr * BO + (size_t)q * L_out;
+          // shared-space byte address of every group's block row (0: absent), once per row
+          const unsigned stage_addr = sm_base + (unsigned)(st * stage_doubles) * 8u;
+          for (unsigned c = lane; c < L_out; c += 32u) {
+            const bool a_ok = (rk & 1) && c < L_prod;
+            double prod = 0.0;
+            if (a_ok) {
+              double total_v = 0.0, inner = 0.0;
+              bool open = false;
+              unsigned gaddr = 0;
+              int g = -1;
+#pragma unroll
+              for (int t = 0; t < NT; t++) {
+                if (t < p.nt) {
+                  if (p.group_start[t]) {
+                    if (open) total_v = __dadd_rn(total_v, inner);
+                    inner = 0.0;
+                    g++;
+                    const unsigned pr = r * ng + g;
+                    const unsigned char sh = s_shift[st][pr];
+                    open = sh != 255;                        // absent source block: the group is skipped
+                    gaddr = stage_addr + (pr * bp.slot + sh + qoff) * 8u;
+                  }
+                  const unsigned cc = c - (unsigned)p.m[t][ne - 1];
+                  if (open && cc < L_src) inner = __dadd_rn(inner, __dmul_rn(lds_f64(gaddr + cc * 8u), sv[t]));
+                }
+              }
+              if (open) total_v = __dadd_rn(total_v, inner);
+              prod = total_v;
+            }
+            double rv;
+            if (bp.add_mode == 0) rv = prod;
+            else if (bp.add_mode == 2) rv = (sr == 0 && q == 0 && c == 0) ? __dadd_rn(prod, slice_base[0]) : prod;
+            else {
+              rv = 0.0;
+              if (a_ok) rv = __dadd_rn(rv, prod);
+              if (b_row && c < p.slice[ne - 1]) rv = __dadd_rn(rv, slice_base[so + (long long)c * p.selfstr[ne - 1]]);
+            }
+            drow[c] = rv;
+          }
+        }
+        mbar_arrive(&s_empty[st]);                           // this consumer is done with the stage
+      }
+    }
+    n_batches_done += nb;
+#pragma unroll
+    for (int a = 0; a < HN_MAXE; a++) cur[a] = nxt[a];
+    src = dst;
+    if (step + 1 < p.nsteps) grid_barrier(p.bar, phase);
+  }
+}
+
+// Fills the group tables from the (sorted) terms of `p` and launches k_horner_rows; false: outside its domain.
+static bool launch_rows_variant(Ctx& ctx, const HornerP& p, int add_mode, const unsigned* final_shape, u64 final_total, const char* tag) {
+  if (!ctx.use_bulk || p.ne < 2) return false;
+  const unsigned L_final = final_shape[p.ne - 1];
+  if (L_final < 16 || L_final > 2048 || final_total < (1u << 18)) return false;
+  if ((reinterpret_cast<uintptr_t>(p.res0) & 15u) || (reinterpret_cast<uintptr_t>(p.buf[0]) & 15u) || (reinterpret_cast<uintptr_t>(p.buf[1]) & 15u)) return false;
+  HornerBulkP bp;
+  memset(&bp, 0, sizeof(bp));
+  bp.h = p;
+  bp.add_mode = add_mode;
+  int ng = 0;
+  for (int t = 0; t < p.nt; t++) {
+    if (p.group_start[t]) {
+      if (ng == HB_MAXG) return false;
+      for (int e = 0; e < p.ne - 1; e++) bp.gm[ng][e] = p.m[t][e];
+      bp.g_first[ng] = (unsigned char)t;
+      bp.g_count[ng] = 0;
+      ng++;
+    }
+    bp.g_count[ng - 1]++;
+  }
+  bp.ng = ng;
+  // Row block: trailing axes on which the substitution is constant and the slice is no longer than the incoming value are
+  // merged with the last axis while the block stays <= 1024 coefficients -- one bulk copy then covers several short rows
+  // (16^6 x [2,1,2,1,1,2]: 16 rows of 16).  On those axes product, result and source extents coincide at every step.
+  int ra = p.ne - 1;
+  u64 block = L_final;
+  while (ra > 0) {
+    const int a = ra - 1;
+    if (p.sshape[a] != 1 || p.slice[a] > p.shape0[a] || final_shape[a] != p.shape0[a]) break;
+    bool offs = false;
+    for (int t = 0; t < p.nt; t++) offs |= p.m[t][a] != 0;
+    if (offs || block * final_shape[a] > 1024) break;
+    block *= final_shape[a];
+    ra = a;
+  }
+  if (ra < 1 || block < 64) return false;       // short rows that cannot be merged: per-copy overhead dominates
+  bp.ra = ra;
+  bp.slot = (unsigned)((block + 3) & ~1ull);
+  int R = (int)std::max<u64>(1, std::min<u64>(HB_R, (24 * 1024 / 8) / ((u64)ng * bp.slot)));   // <= 24 KB per stage
+  bp.R = R;
+  const size_t smem = (size_t)HB_NS * R * ng * bp.slot * sizeof(double);
+  if (smem > 200 * 1024) return false;
+  static int coop[64] = {};
+  int& c = coop[ctx.device & 63];
+  if (c == 0) {
+    int vv = 0;
+    cudaDeviceGetAttribute(&vv, cudaDevAttrCooperativeLaunch, ctx.device);
+    c = vv ? 1 : -1;
+  }
+  if (c < 0) return false;
+  const void* fn;
+  int bucket;
+  if (p.nt <= 2) { fn = (const void*)k_horner_rows<2>; bucket = 0; }
+  else if (p.nt <= 4) { fn = (const void*)k_horner_rows<4>; bucket = 1; }
+  else if (p.nt <= 8) { fn = (const void*)k_horner_rows<8>; bucket = 2; }
+  else if (p.nt <= 16) { fn = (const void*)k_horner_rows<16>; bucket = 3; }
+  else { fn = (const void*)k_horner_rows<32>; bucket = 4; }
+  static size_t configured[5][64] = {};
+  if (configured[bucket][ctx.device & 63] < smem) {
+    GTP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[bucket][ctx.device & 63] = smem;
+  }
+  int per_sm = 0;
+  GTP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, HB_T, smem));
+  if (per_sm < 1) return false;
+  const u64 nsr = final_total / block;
+  const unsigned grid = (unsigned)std::max<u64>(1, std::min<u64>((nsr + R - 1) / R, (u64)std::min(per_sm, 4) * ctx.sm_count));
+  void* args[] = {(void*)&bp};
+  const double t0 = ctx.hist ? Ctx::now() : 0.0;
+  GTP_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(HB_T), args, smem, ctx.stream));
+  ctx.launches++;
+  if (ctx.hist) {
+    (*ctx.hist)[tag]++;
+    ctx.t_launch += Ctx::now() - t0;
+  }
+  return true;
+}
+
 // Host side.  `self`: the polynomial whose axis v is substituted (shape self_shape, already zero-extended to the common
 // ndim), `d`: result degrees, `subst`: shape sshape (<= 32 coefficients, <= d), `res`: the running Horner value (shape
 // rshape) BEFORE the step that adds slice i_top.  Runs the steps i_top, i_top-1, .., 0 and returns the final buffer and
@@ -236,6 +580,13 @@ bool launch_horner(Ctx& ctx, const double* self, const Shape& self_shape, u64 v,
   p.buf[0] = b0->d;
   p.buf[1] = b1 ? b1->d : b0->d;
   p.bar = reinterpret_cast<unsigned*>(bar->d);
+  *out_buf = ((nsteps - 1) & 1) ? b1 : b0;
+  *out_shape = cur;
+  {
+    unsigned fs[HN_MAXE];
+    for (int e = 0; e < ne; e++) fs[e] = (unsigned)cur[eff[e]];
+    if (launch_rows_variant(ctx, p, p.slice_scalar ? 2 : 1, fs, final_total, "k_horner_rows")) return true;
+  }
   static int coop[64] = {};
   int& c = coop[ctx.device & 63];
   if (c == 0) {
@@ -267,6 +618,82 @@ bool launch_horner(Ctx& ctx, const double* self, const Shape& self_shape, u64 v,
   *out_buf = ((nsteps - 1) & 1) ? b1 : b0;
   *out_shape = cur;
   return true;
+}
+
+// The plain small-operand product (launch_mul_stencil's case, kernels_mul.cu) on the row-staged kernel: one "step" without
+// the Add.  false: outside the domain (the caller continues with the gather kernels).
+bool launch_stencil_rows(Ctx& ctx, const MulArgs& a) {
+  const int nd = a.ndim;
+  if (a.accumulate || !a.rows.empty() || nd < 2 || a.row_begin != 0 || a.row_step != 1 || a.row_count != a.rs[0]) return false;
+  const u64 nx = prod(a.xs), ny = prod(a.ys);
+  const bool small_is_x = nx <= ny;
+  const Shape& ss = small_is_x ? a.xs : a.ys;
+  const Shape& bs = small_is_x ? a.ys : a.xs;
+  const u64 ns = std::min(nx, ny);
+  if (ns < 1 || ns > (u64)HN_MAXT) return false;
+  std::vector<int> eff;
+  for (int d = 0; d < nd; d++) {
+    if (a.rs[d] == 1) {
+      if (a.xs[d] != 1 || a.ys[d] != 1) return false;
+      continue;
+    }
+    if (a.rs[d] > bs[d] + ss[d] - 1 || ss[d] > 255) return false;   // no rows / columns beyond the product's own extent
+    eff.push_back(d);
+  }
+  const int ne = (int)eff.size();
+  if (ne < 2 || ne > HN_MAXE) return false;
+  const u64 total = prod(a.rs);
+  if (total >= (1ull << 31) || prod(bs) >= (1ull << 31)) return false;
+  HornerP p;
+  memset(&p, 0, sizeof(p));
+  p.ne = ne;
+  Shape sst(nd, 1);
+  for (int d = nd - 2; d >= 0; --d) sst[d] = sst[d + 1] * ss[d + 1];
+  unsigned fs[HN_MAXE];
+  for (int e = 0; e < ne; e++) {
+    const int d = eff[e];
+    p.d[e] = (unsigned)a.rs[d];
+    p.sshape[e] = (unsigned)ss[d];
+    p.slice[e] = 1;
+    p.shape0[e] = (unsigned)bs[d];
+    fs[e] = (unsigned)a.rs[d];
+  }
+  struct Term { std::vector<unsigned> m; u64 idx; };
+  std::vector<Term> terms;
+  for (u64 lin = 0; lin < ns; lin++) {
+    u64 rem = lin;
+    std::vector<unsigned> full(nd);
+    for (int d = nd - 1; d >= 0; --d) { full[d] = (unsigned)(rem % ss[d]); rem /= ss[d]; }
+    bool ok = true;
+    for (int d = 0; d < nd; d++)
+      if (a.rs[d] == 1 && full[d] != 0) ok = false;
+    if (!ok) continue;
+    Term t;
+    t.idx = lin;
+    for (int e = 0; e < ne; e++) t.m.push_back(full[eff[e]]);
+    terms.push_back(t);
+  }
+  if (terms.empty()) return false;
+  // ascending X index: ascending m if the small operand is X, descending if it is Y (as launch_mul_stencil)
+  std::sort(terms.begin(), terms.end(), [&](const Term& x, const Term& y) { return small_is_x ? x.m < y.m : x.m > y.m; });
+  p.nt = (int)terms.size();
+  for (int t = 0; t < p.nt; t++) {
+    for (int e = 0; e < ne; e++) p.m[t][e] = (unsigned char)terms[t].m[e];
+    p.sidx[t] = (unsigned short)terms[t].idx;
+    bool new_group = t == 0;
+    for (int e = 0; e < ne - 1 && !new_group; e++) new_group = terms[t].m[e] != terms[t - 1].m[e];
+    p.group_start[t] = new_group ? 1 : 0;
+  }
+  p.self = small_is_x ? a.y : a.x;    // unused (no Add), any valid pointer
+  p.subst = small_is_x ? a.x : a.y;
+  p.res0 = small_is_x ? a.y : a.x;
+  p.buf[0] = p.buf[1] = a.out;
+  p.i_top = 0;
+  p.nsteps = 1;
+  BufP bar = ctx.alloc(2);
+  GTP_CUDA(cudaMemsetAsync(bar->d, 0, 16, ctx.stream));
+  p.bar = reinterpret_cast<unsigned*>(bar->d);
+  return launch_rows_variant(ctx, p, 0, fs, total, "k_horner_rows<product>");
 }
 
 }  // namespace gtp

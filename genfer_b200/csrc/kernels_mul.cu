@@ -135,6 +135,7 @@ void launch_mul_blk(Ctx& ctx, const MulArgs& a);
 bool slide_mul_applicable(const Ctx& ctx, const MulArgs& a);
 void launch_mul_slide(Ctx& ctx, const MulArgs& a);
 bool launch_mul_axis(Ctx& ctx, const MulArgs& a);   // kernels_mul_axis.cu
+bool launch_stencil_rows(Ctx& ctx, const MulArgs& a);   // kernels_horner.cu: row-staged (bulk-copy) small-operand product
 
 // 0: reference-order kernel, 2: 2x2-blocked DFMA kernel (kernels_mul_blk.cu), 3: sliding 1x2 DFMA kernel for dense
 // cube slabs (kernels_mul_slide.cu).  (1 was the cube-16-only kernel of
@@ -371,6 +372,10 @@ static bool launch_mul_stencil(Ctx& ctx, const MulArgs& a) {
   if (total == 0 || total >= (1ull << 32) - 65536 || a.row_begin + a.row_count * a.row_step >= (1ull << 32)) return false;
   for (int d = 0; d < nd; d++)
     if (ss[d] > 255) return false;
+  // The row-staged bulk-copy kernel (kernels_horner.cu) wins inside the fused Horner loop (0.138 s against 0.202 s on
+  // population_50_3vars --limit 300) but not on a single product, where the four-coefficient gather below is 2x faster
+  // (0.139 ms against 0.269 ms on [297,282,297] x [2,1,2], profiles/r02_stencil_ab.txt): opt-in for A/B measurements.
+  if (ctx.bulk_products && launch_stencil_rows(ctx, a)) return true;
   StencilP p;
   memset(&p, 0, sizeof(p));
   Shape sst(nd, 1), bst(nd, 1);

@@ -152,6 +152,26 @@ def test_axis_convolution_kernel_is_bit_exact(ctx, xs, ys, rs):
     assert np.array_equal(got.view(np.uint64), ref.view(np.uint64))
 
 
+STENCIL_ROWS = [((97, 83, 91), (2, 1, 2), (98, 83, 92)), ((2, 1, 2), (97, 83, 91), (98, 83, 92)), ((120, 130, 75), (2, 2, 2), (121, 131, 76)),
+                ((300, 1000), (3, 2), (300, 1001)), ((31, 29, 1, 33, 35), (2, 1, 1, 1, 2), (32, 29, 1, 33, 36)),
+                ((97, 83, 91), (2, 1, 2), (90, 80, 91)), ((16,) * 6, (2, 1, 2, 1, 1, 2), (17, 16, 17, 16, 16, 17)),
+                ((40, 9, 8, 7), (2, 1, 1, 3), (41, 9, 8, 9))]
+
+
+@pytest.mark.parametrize("xs,ys,rs", STENCIL_ROWS)
+def test_row_staged_small_operand_product_is_bit_exact(ctx, xs, ys, rs):
+    """The row-staged bulk-copy (TMA) kernel of the fused Horner loop (k_horner_rows), driven as a single product: same
+    bits as the reference order, either operand order, truncated results, unit axes, odd row lengths, merged row blocks."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(sum(rs))
+    x, y = rng.standard_normal(xs), rng.standard_normal(ys)
+    ref = O.mul_raw(x, y, rs)
+    got = gpu_mul_raw(ctx, x, y, rs, fast=1 + 32768)     # the row-staged kernel (opt-in for single products)
+    assert np.array_equal(got.view(np.uint64), ref.view(np.uint64))
+    got = gpu_mul_raw(ctx, x, y, rs, fast=True)          # default: the gather kernels give the same bits
+    assert np.array_equal(got.view(np.uint64), ref.view(np.uint64))
+
+
 ODD_SHAPES = [((27,) * 3,) * 3, ((13,) * 4,) * 3, ((17,) * 4,) * 3, ((31,) * 3,) * 3, ((9,) * 5,) * 3,
               ((13, 17, 19, 21), (11, 17, 15, 21), (13, 17, 19, 21)), ((5, 27, 27, 27), (3, 20, 27, 25), (7, 27, 27, 27))]
 

@@ -375,7 +375,10 @@ HORNER_CASES = [  # (self shape, degrees, substituted axis, subst shape)
     ((9, 8, 7), (12, 11, 10), 2, (2, 1, 2)), ((9, 8, 7), (12, 11, 10), 0, (2, 2, 1)), ((20, 6), (24, 9), 0, (2, 2)),
     ((6, 20), (9, 24), 1, (1, 3)), ((6, 20), (9, 24), 1, (3, 1)), ((30,), (40,), 0, (3,)), ((5, 4, 3, 6), (6, 6, 6, 6), 3, (2, 1, 1, 2)),
     ((40, 50, 45), (60, 60, 60), 2, (2, 1, 2)), ((7, 5), (7, 5), 1, (4, 5)), ((12, 3), (30, 30), 1, (2, 3)),
-    ((33, 1, 9), (40, 5, 12), 2, (1, 2, 2))]
+    ((33, 1, 9), (40, 5, 12), 2, (1, 2, 2)),
+    # HBM / L2-sized: the row-staged bulk-copy (TMA) variant -- odd row lengths (shifted, odd-tailed rows), 2 and 4 groups
+    ((70, 60, 80), (91, 85, 97), 2, (2, 1, 2)), ((64, 70, 66), (90, 90, 90), 0, (2, 2, 1)), ((50, 300), (400, 700), 0, (2, 2)),
+    ((30, 20, 25, 40), (33, 33, 33, 47), 1, (2, 1, 2, 2))]
 
 
 @pytest.mark.parametrize("shape,deg,v,sshape", HORNER_CASES)

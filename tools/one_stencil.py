@@ -1,0 +1,23 @@
+"""Developer tool: a few launches of the small-operand product on [297,282,297] x [2,1,2] (ncu target)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, genfer_b200
+mode = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
+ctx = genfer_b200.Context(0, stream=stream.cuda_stream)
+ctx.set_fast_mul(mode)
+TP = genfer_b200.TaylorPoly
+xs, ys = (297, 282, 297), (2, 1, 2)
+rs = tuple(a + b - 1 for a, b in zip(xs, ys))
+big = torch.rand(xs, dtype=torch.float64, device="cuda"); small = torch.rand(ys, dtype=torch.float64, device="cuda")
+B = TP.from_device(big.data_ptr(), xs, rs, ctx); S = TP.from_device(small.data_ptr(), ys, rs, ctx)
+for _ in range(4):
+    Z = B * S
+torch.cuda.synchronize()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(10):
+    Z = B * S
+b.record(); torch.cuda.synchronize()
+print("ms per product", a.elapsed_time(b) / 10)
+ctx.close()
