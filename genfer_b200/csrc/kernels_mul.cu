@@ -29,8 +29,18 @@ struct MulP {
   int accumulate;
 };
 
+template <int NE> __device__ __forceinline__ void mul_ordered_body(const MulP& p);
 template <int NE>
-__global__ void __launch_bounds__(128) k_mul_ordered(const MulP p) {
+__global__ void __launch_bounds__(128) k_mul_ordered(const MulP p) { mul_ordered_body<NE>(p); }
+// Single-CTA variant for small results (<= 1024 coefficients): the producer classifies its own output (extract_linear scan,
+// kernels.cuh::cls_epilogue) instead of a separate classification launch + wait by the next operator's dispatch.
+template <int NE>
+__global__ void __launch_bounds__(1024) k_mul_ordered_cls(const MulP p, const FusedClsArgs cls) {
+  mul_ordered_body<NE>(p);
+  if (cls.slot) cls_epilogue(p.out, cls.p, cls.slot, cls.seq);
+}
+template <int NE>
+__device__ __forceinline__ void mul_ordered_body(const MulP& p) {
   const u64 gstride = (u64)gridDim.x * blockDim.x;
   for (u64 lin = (u64)blockIdx.x * blockDim.x + threadIdx.x; lin < p.total; lin += gstride) {
     unsigned k[NE], lo[NE], hi[NE];
@@ -207,6 +217,19 @@ static void launch_mul_ordered(Ctx& ctx, const MulArgs& a) {
   p.out = a.out;
   p.accumulate = a.accumulate ? 1 : 0;
   if (p.total == 0) return;
+  // small whole results: one CTA that also classifies what it wrote
+  if (p.total <= 1024 && !a.accumulate && a.row_begin == 0 && a.row_step == 1 && (nd == 0 || a.rs[0] == 1 || a.row_count == a.rs[0])) {
+    FusedClsArgs cls;
+    if (fused_cls_begin(ctx, a.out, a.rs, &cls)) {
+      const int blk = (int)std::min<u64>(1024, (p.total + 31) / 32 * 32);
+      switch (ne) {
+#define CASE(N) case N: GTP_LAUNCH(ctx, k_mul_ordered_cls<N>, 1, blk, 0, p, cls); break;
+        CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+#undef CASE
+      }
+      return;
+    }
+  }
   int block = 128;
   int grid = (int)std::max<u64>(1, std::min<u64>((p.total + block - 1) / block, (u64)ctx.sm_count * 64));
   switch (ne) {

@@ -43,6 +43,10 @@ from genfer_b200.synth import splitmix64, synth_pgf, synth_uniform  # noqa: E402
 # ---------------------------------------------------------------------------------------------
 # north_star check 2, end to end: f64 results inside the Interval<F64> enclosure of the same evaluation
 # ---------------------------------------------------------------------------------------------
+# programs whose Interval<F64> evaluation takes more than a few seconds on one host core: left out of the CPU suite (kept to a
+# few minutes); the GPU suite (-m gpu) checks the BASELINE programs among them too (ENCLOSURE_GPU_EXTRA: 20-60 s of oracle each)
+ENCLOSURE_GPU_EXTRA = ("real_world/population2000.sgcl", "real_world/population_modified2000.sgcl", "real_world/population_2000_1vars.sgcl",
+                       "real_world/switchpoint.sgcl", "real_world/cont_switchpoint.sgcl", "real_world/hmm.sgcl", "slow/two_populations2000.sgcl")
 ENCLOSURE_SLOW = {"mixture", "hmm", "switchpoint", "cont_switchpoint", "two_populations2000", "two_populations", "nested_infer_expensive",
                   "population_modified2000", "population2000", "population_2000_1vars", "population", "population_modified"}
 

@@ -64,9 +64,11 @@ def test_gpu_matches_reference_golden(ctx, rel):
 
 
 def enclosure_fixtures():
-    from helpers import ENCLOSURE_SLOW
-    return [rel for rel in fixtures() if os.path.basename(rel)[:-5] not in ENCLOSURE_SLOW
+    from helpers import ENCLOSURE_GPU_EXTRA, ENCLOSURE_SLOW
+    fast = [rel for rel in fixtures() if os.path.basename(rel)[:-5] not in ENCLOSURE_SLOW
             and os.path.getsize(os.path.join(GOLD, rel)) < 50_000]
+    # BASELINE configs C2 / C3 (population*, two_populations, switchpoint, hmm): the enclosure run costs the oracle 20-60 s each
+    return fast + [rel for rel in ENCLOSURE_GPU_EXTRA if os.path.exists(os.path.join(GOLD, rel)) and rel not in fast]
 
 
 @pytest.mark.parametrize("rel", enclosure_fixtures())
