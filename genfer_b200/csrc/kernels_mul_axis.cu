@@ -168,12 +168,20 @@ bool launch_mul_axis(Ctx& ctx, const MulArgs& a) {
     GTP_LAUNCH(ctx, k_mul_axis_row, grid, AX_TB, smem, p);
     return true;
   }
-  constexpr int KT = 8;
+  // outputs per thread along the axis: 8 when that still gives every SM a few hundred threads, fewer for small tensors
+  // ([336] x [336, 336]: KT = 8 left 14 k threads, each a chain of 336 dependent steps: 95 us; latency-bound)
   const u64 ncol = outer * inner;
+  int KT = 8;
+  while (KT > 1 && ncol * ((Lr + KT - 1) / KT) < (u64)ctx.sm_count * 512) KT /= 2;
   const u64 ktiles = (Lr + KT - 1) / KT;
   if (ktiles > 65535) return false;
   dim3 grid((unsigned)((ncol + 127) / 128), (unsigned)ktiles);
-  GTP_LAUNCH(ctx, k_mul_axis_cols<KT>, grid, 128, 0, p);
+  switch (KT) {
+    case 8: GTP_LAUNCH(ctx, k_mul_axis_cols<8>, grid, 128, 0, p); break;
+    case 4: GTP_LAUNCH(ctx, k_mul_axis_cols<4>, grid, 128, 0, p); break;
+    case 2: GTP_LAUNCH(ctx, k_mul_axis_cols<2>, grid, 128, 0, p); break;
+    default: GTP_LAUNCH(ctx, k_mul_axis_cols<1>, grid, 128, 0, p); break;
+  }
   return true;
 }
 
