@@ -67,7 +67,8 @@ int gtp_ctx_trim(gtp_ctx* ctx);
 void* gtp_ctx_stream(gtp_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t gtp_ctx_launch_count(gtp_ctx* ctx);
-/* tuning knob: 0 = always use the reference-order product kernel and the wavefront division (exact order),
+/* tuning knob: 0 = always use the reference-order product kernel (bit-identical products, Horner loops and 2-axis log / exp;
+ * general N-D division and N-D log stay tolerance-level: their wavefront / descending-row summation order is not the reference's),
  * 1 = pick the fastest applicable kernel (default: DFMA kernels from 2^20 MACs), 2 = use the DFMA kernels even for
  * tiny products (tests).  A/B bits: +4 evenly dealt instead of folded item tables (blocked kernel), +8 octet tables
  * (experimental), +16 sliding kernel off, +32 / +64 force the plane-tiled sliding plan with 4 / 8 planes per slab,

@@ -472,6 +472,53 @@ def test_recurrences_with_ragged_operands(G):
         assert_close(gy.log(), oy.log(), rtol=1e-12)
 
 
+def test_recurrence_kernel_edge_shapes(G):
+    """Shortest rows, seven leaf axes, a row longer than one CTA's threads, arguments shorter than the result."""
+    rng = np.random.default_rng(2024)
+    for shape, deg in (((2, 2), None), ((2,) * 8, None), ((2, 1500), (3, 1600)), ((3, 2, 2), (9, 9, 9)), ((1, 4, 1, 3), (2, 5, 2, 4))):
+        a = rng.uniform(0.5, 1.5, shape)
+        x = rng.standard_normal(shape)
+        ga, oa = both(G, a, deg)
+        gx, ox = both(G, x, deg)
+        assert_close(ga.exp(), oa.exp(), rtol=1e-12)
+        assert_close(ga.log(), oa.log(), rtol=1e-12)
+        assert_close(gx / ga, ox / oa, rtol=1e-12)
+
+
+def test_fused_horner_with_unbounded_degrees_and_32_terms(G):
+    """`simplify` runs subst_var with degrees_p1 = usize::MAX (exact polynomial algebra, generating_function.rs:485, :569);
+    a 2^5-coefficient substitution is the largest the fused loop takes."""
+    from genfer_b200 import UNBOUNDED
+    rng = np.random.default_rng(11)
+    a = rng.standard_normal((3, 4, 5))
+    sub = rng.standard_normal((2, 2, 2))
+    g, o = G.TaylorPoly.new(a, [UNBOUNDED] * 3), O().TaylorPoly.new(a, [O().UMAX] * 3)
+    gs, os_ = G.TaylorPoly.new(sub, [UNBOUNDED] * 3), O().TaylorPoly.new(sub, [O().UMAX] * 3)
+    for v in range(3):
+        assert_same(g.subst_var(v, gs), o.subst_var(v, os_))
+    a5 = rng.standard_normal((3, 3, 3, 3, 4))
+    s5 = rng.standard_normal((2, 2, 2, 2, 2))
+    g, o = both(G, a5, (5, 5, 5, 5, 6))
+    gs, os_ = both(G, s5, (5, 5, 5, 5, 6))
+    assert_same(g.subst_var(4, gs), o.subst_var(4, os_))
+
+
+def test_pinned_upload_and_trim(G):
+    """gtp_from_host may be handed pinned memory that is overwritten as soon as the call returns (advisor finding, round 1);
+    gtp_ctx_trim returns the cached blocks and the context keeps working."""
+    import torch
+    ctx = G.default_context()
+    h = torch.arange(1 << 20, dtype=torch.float64).pin_memory()
+    expect = h.numpy().copy()
+    t = G.TaylorPoly.from_host_ptr(h.data_ptr(), (1 << 10, 1 << 10), (1 << 10, 1 << 10), ctx)
+    h.fill_(-1.0)                                   # reuse the staging buffer at once
+    assert np.array_equal(t.array().ravel(), expect)
+    del t
+    ctx.check(ctx.lib.gtp_ctx_trim(ctx.h))
+    u = G.TaylorPoly.new(expect[:100], (100,), ctx)
+    assert np.array_equal((u + u).array(), 2 * expect[:100])
+
+
 # ---------------------------------------------------------------------------------------------
 # north_star check 2: the f64 results lie inside the --bounds (Interval<F64>) enclosure
 # ---------------------------------------------------------------------------------------------
