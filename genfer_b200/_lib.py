@@ -100,6 +100,39 @@ _SIGS = {
     "gtp_sgcl_is_normalized": (C.c_int, [vp]),
     "gtp_sgcl_probs": (None, [vp, f64p, f64p]),
     "gtp_sgcl_stats": (None, [vp, u64p, u64p]),
+    "gtp_run_sgcl_bounds": (C.c_int, [vp, C.c_char_p, C.c_int64, C.c_uint64, f64p, f64p, C.c_char_p, C.c_size_t]),
+    "gti_from_scalar": (C.c_int, [vp, C.c_double, C.c_double, vpp]),
+    "gti_zero_with": (C.c_int, [vp, C.c_int, u64p, vpp]),
+    "gti_var": (C.c_int, [vp, C.c_uint64, C.c_double, C.c_double, C.c_uint64, vpp]),
+    "gti_var_at_zero": (C.c_int, [vp, C.c_uint64, C.c_uint64, vpp]),
+    "gti_var_with_degrees_p1": (C.c_int, [vp, C.c_uint64, C.c_double, C.c_double, C.c_int, u64p, vpp]),
+    "gti_from_host": (C.c_int, [vp, C.c_int, u64p, u64p, vp, C.c_int, vpp]),
+    "gti_to_host": (C.c_int, [vp, vp, vp]),
+    "gti_free": (None, [vp, vp]),
+    "gti_ndim": (C.c_int, [vp]),
+    "gti_len": (C.c_uint64, [vp]),
+    "gti_shape": (None, [vp, u64p]),
+    "gti_degrees_p1": (None, [vp, u64p]),
+    "gti_add": (C.c_int, [vp, vp, vp, vpp]),
+    "gti_sub": (C.c_int, [vp, vp, vp, vpp]),
+    "gti_mul": (C.c_int, [vp, vp, vp, vpp]),
+    "gti_div": (C.c_int, [vp, vp, vp, vpp]),
+    "gti_neg": (C.c_int, [vp, vp, vpp]),
+    "gti_exp": (C.c_int, [vp, vp, vpp]),
+    "gti_log": (C.c_int, [vp, vp, vpp]),
+    "gti_pow": (C.c_int, [vp, vp, C.c_uint32, vpp]),
+    "gti_derivative": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, vpp]),
+    "gti_taylor_expansion_of_coeff": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, vpp]),
+    "gti_shift_down": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, vpp]),
+    "gti_coefficients_of_term": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, vpp]),
+    "gti_taylor_polynomial_terms": (C.c_int, [vp, vp, C.c_uint64, u64p, C.c_int, vpp]),
+    "gti_subst_var": (C.c_int, [vp, vp, C.c_uint64, vp, vpp]),
+    "gti_truncate_to_degree_p1": (C.c_int, [vp, vp, C.c_uint64, vpp]),
+    "gti_remove_last_variable": (C.c_int, [vp, vp, vpp]),
+    "gti_extend_to_dim": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, vpp]),
+    "gti_constant_term": (C.c_int, [vp, vp, f64p]),
+    "gti_extract_constant": (C.c_int, [vp, vp, intp, f64p]),
+    "gti_gather_axis": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, vp]),
     "gtu_constant": (C.c_int, [vp, C.c_double, vpp]),
     "gtu_from_coefficients": (C.c_int, [vp, f64p, C.c_uint64, vpp]),
     "gtu_var": (C.c_int, [vp, C.c_double, C.c_uint64, vpp]),

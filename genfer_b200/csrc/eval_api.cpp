@@ -9,6 +9,7 @@
 
 #include "../../include/genfer_taylor.h"
 #include "evaluator/report.hpp"
+#include "interval.cuh"
 
 namespace {
 
@@ -87,6 +88,100 @@ struct GpuBackend {
   }
 };
 
+// Interval<F64> as the evaluator sees it (src/interval.rs): constructible from an f64 constant (a point interval); the
+// arithmetic is interval.cuh's, the same functions the kernels run.
+struct IvS {
+  gti::Iv v{0.0, 0.0};
+  IvS() = default;
+  IvS(double x) : v{x, x} {}
+  explicit IvS(gti::Iv i) : v(i) {}
+  friend IvS operator+(const IvS& a, const IvS& b) { return IvS(gti::iv_add(a.v, b.v)); }
+  friend IvS operator-(const IvS& a, const IvS& b) { return IvS(gti::iv_sub(a.v, b.v)); }
+  friend IvS operator*(const IvS& a, const IvS& b) { return IvS(gti::iv_mul(a.v, b.v)); }
+  friend IvS operator/(const IvS& a, const IvS& b) { return IvS(gti::iv_div(a.v, b.v)); }
+  friend bool operator==(const IvS& a, const IvS& b) { return a.v.lo == b.v.lo && a.v.hi == b.v.hi; }
+};
+
+// TaylorPoly<Interval<F64>> on the device (gti_*, interval_api.cu): the number type of the reference's --bounds mode
+struct GpuIvBackend {
+  gtp_ctx* ctx;
+  struct Handle {
+    gtp_ctx* c;
+    gti_poly* p;
+    Handle(gtp_ctx* c_, gti_poly* p_) : c(c_), p(p_) {}
+    ~Handle() { if (p) gti_free(c, p); }
+    Handle(const Handle&) = delete;
+    Handle& operator=(const Handle&) = delete;
+  };
+  using Poly = std::shared_ptr<Handle>;
+  using Scalar = IvS;
+  static IvS scalar_max(const IvS& x, const IvS& y) {   // Interval::max: componentwise
+    return IvS(gti::iv(x.v.lo > y.v.lo ? x.v.lo : y.v.lo, x.v.hi > y.v.hi ? x.v.hi : y.v.hi));
+  }
+  void check(int rc) const {
+    if (rc != 0) throw gfe::EvalError(std::string("libgenfer_taylor: ") + gtp_last_error(ctx));
+  }
+  Poly wrap(gti_poly* p) const { return std::make_shared<Handle>(ctx, p); }
+
+  Poly from_scalar(const IvS& x) { gti_poly* o; check(gti_from_scalar(ctx, x.v.lo, x.v.hi, &o)); return wrap(o); }
+  Poly var(gfe::Var v, const IvS& x, size_t len) { gti_poly* o; check(gti_var(ctx, v, x.v.lo, x.v.hi, len, &o)); return wrap(o); }
+  Poly var_at_zero(gfe::Var v, size_t len) { gti_poly* o; check(gti_var_at_zero(ctx, v, len, &o)); return wrap(o); }
+  Poly var_with_degrees(gfe::Var v, const IvS& x, const std::vector<uint64_t>& d) {
+    gti_poly* o; check(gti_var_with_degrees_p1(ctx, v, x.v.lo, x.v.hi, (int)d.size(), d.data(), &o)); return wrap(o);
+  }
+  Poly zero_with(const std::vector<uint64_t>& d) { gti_poly* o; check(gti_zero_with(ctx, (int)d.size(), d.data(), &o)); return wrap(o); }
+  Poly new_poly(const std::vector<uint64_t>& shape, const std::vector<uint64_t>& degrees, const double* data) {   // f64 GenFun constants
+    gti_poly* o; check(gti_from_host(ctx, (int)shape.size(), shape.data(), degrees.data(), data, 0, &o)); return wrap(o);
+  }
+  Poly new_poly(const std::vector<uint64_t>& shape, const std::vector<uint64_t>& degrees, const IvS* data) {
+    static_assert(sizeof(IvS) == 2 * sizeof(double), "IvS is a (lo, hi) pair");
+    gti_poly* o; check(gti_from_host(ctx, (int)shape.size(), shape.data(), degrees.data(), reinterpret_cast<const double*>(data), 1, &o)); return wrap(o);
+  }
+#define GFE_BIN(name, fn) Poly name(const Poly& a, const Poly& b) { gti_poly* o; check(fn(ctx, a->p, b->p, &o)); return wrap(o); }
+  GFE_BIN(add, gti_add) GFE_BIN(sub, gti_sub) GFE_BIN(mul, gti_mul) GFE_BIN(div, gti_div)
+#undef GFE_BIN
+  Poly neg(const Poly& a) { gti_poly* o; check(gti_neg(ctx, a->p, &o)); return wrap(o); }
+  Poly exp(const Poly& a) { gti_poly* o; check(gti_exp(ctx, a->p, &o)); return wrap(o); }
+  Poly log(const Poly& a) { gti_poly* o; check(gti_log(ctx, a->p, &o)); return wrap(o); }
+  Poly pow(const Poly& a, uint32_t e) { gti_poly* o; check(gti_pow(ctx, a->p, e, &o)); return wrap(o); }
+  Poly derivative(const Poly& a, gfe::Var v, size_t n) { gti_poly* o; check(gti_derivative(ctx, a->p, v, n, &o)); return wrap(o); }
+  Poly taylor_expansion_of_coeff(const Poly& a, gfe::Var v, size_t n) { gti_poly* o; check(gti_taylor_expansion_of_coeff(ctx, a->p, v, n, &o)); return wrap(o); }
+  Poly shift_down(const Poly& a, gfe::Var v, size_t n) { gti_poly* o; check(gti_shift_down(ctx, a->p, v, n, &o)); return wrap(o); }
+  Poly coefficients_of_term(const Poly& a, gfe::Var v, size_t n) { gti_poly* o; check(gti_coefficients_of_term(ctx, a->p, v, n, &o)); return wrap(o); }
+  Poly taylor_polynomial_terms(const Poly& a, gfe::Var v, const std::vector<size_t>& orders) {
+    std::vector<uint64_t> os(orders.begin(), orders.end());
+    gti_poly* o; check(gti_taylor_polynomial_terms(ctx, a->p, v, os.data(), (int)os.size(), &o)); return wrap(o);
+  }
+  Poly subst_var(const Poly& a, gfe::Var v, const Poly& s) { gti_poly* o; check(gti_subst_var(ctx, a->p, v, s->p, &o)); return wrap(o); }
+  Poly truncate_to_degree_p1(const Poly& a, size_t d) { gti_poly* o; check(gti_truncate_to_degree_p1(ctx, a->p, d, &o)); return wrap(o); }
+  Poly remove_last_variable(const Poly& a) { gti_poly* o; check(gti_remove_last_variable(ctx, a->p, &o)); return wrap(o); }
+  Poly extend_to_dim(const Poly& a, size_t ndim, size_t d) { gti_poly* o; check(gti_extend_to_dim(ctx, a->p, ndim, d, &o)); return wrap(o); }
+  IvS constant_term(const Poly& a) { double x[2]; check(gti_constant_term(ctx, a->p, x)); return IvS(gti::iv(x[0], x[1])); }
+  std::vector<IvS> gather_axis(const Poly& a, gfe::Var v, size_t count) {
+    std::vector<IvS> out(count);
+    if (count) check(gti_gather_axis(ctx, a->p, v, count, reinterpret_cast<double*>(out.data())));
+    return out;
+  }
+  size_t num_vars(const Poly& a) { return (size_t)gti_ndim(a->p); }
+  std::vector<uint64_t> array_shape(const Poly& a) {
+    std::vector<uint64_t> s((size_t)gti_ndim(a->p) + 1);
+    gti_shape(a->p, s.data());
+    s.resize((size_t)gti_ndim(a->p));
+    return s;
+  }
+  std::optional<IvS> extract_constant(const Poly& a) {
+    int is_c = 0; double v[2] = {0, 0};
+    check(gti_extract_constant(ctx, a->p, &is_c, v));
+    if (is_c) return IvS(gti::iv(v[0], v[1]));
+    return std::nullopt;
+  }
+  std::vector<IvS> to_host(const Poly& a) {
+    std::vector<IvS> out(gti_len(a->p));
+    check(gti_to_host(ctx, a->p, reinterpret_cast<double*>(out.data())));
+    return out;
+  }
+};
+
 }  // namespace
 
 struct gtp_sgcl_result {
@@ -116,6 +211,37 @@ int gtp_run_sgcl(gtp_ctx* ctx, const char* source, int64_t limit, int flags, uin
       err[err_cap - 1] = '\0';
     }
     return GTP_ERR_INDEX;   // the reference panics on every error of this path (parse error, assert!)
+  }
+}
+// The --bounds-style enclosure of the evaluator's direct outputs with the interval arithmetic on the device: the
+// same host logic over TaylorPoly<Interval<F64>> (gti_*).  GenFun constants are the f64 values of the f64 path, as point
+// intervals; no simplification pass (its polynomial form stores f64 coefficients).
+// out12: [rest lo, hi, total lo, hi, raw moment 1..4 lo, hi]; probs_lohi: `limit` (lo, hi) pairs (may be null when limit <= 0).
+int gtp_run_sgcl_bounds(gtp_ctx* ctx, const char* source, int64_t limit, uint64_t unroll, double* out12, double* probs_lohi,
+                        char* err, size_t err_cap) {
+  if (!ctx || !source || !out12) return GTP_ERR_ARG;
+  try {
+    GpuIvBackend backend{ctx};
+    gfe::Program program = gfe::parse_program(source);
+    gfe::GfTransformer transformer((size_t)unroll);
+    gfe::GfTranslation tr = transformer.semantics(program);
+    gfe::Evaluator<GpuIvBackend> ev(backend);
+    IvS rest = backend.constant_term(ev.eval(tr.rest, std::vector<IvS>(tr.var_info.num_vars(), IvS(0.0)), 1));
+    auto mom = ev.moments_taylor(tr.gf, program.result, tr.var_info, 5);
+    out12[0] = rest.v.lo; out12[1] = rest.v.hi;
+    out12[2] = mom.first.v.lo; out12[3] = mom.first.v.hi;
+    for (size_t i = 0; i < 4; i++) { out12[4 + 2 * i] = mom.second.at(i).v.lo; out12[5 + 2 * i] = mom.second.at(i).v.hi; }
+    if (limit > 0 && probs_lohi) {
+      std::vector<IvS> p = ev.probs_taylor(tr.gf, program.result, tr.var_info, (size_t)limit);
+      for (size_t i = 0; i < (size_t)limit; i++) { probs_lohi[2 * i] = p.at(i).v.lo; probs_lohi[2 * i + 1] = p.at(i).v.hi; }
+    }
+    return GTP_OK;
+  } catch (const std::exception& e) {
+    if (err && err_cap) {
+      std::strncpy(err, e.what(), err_cap - 1);
+      err[err_cap - 1] = '\0';
+    }
+    return GTP_ERR_INDEX;
   }
 }
 void gtp_sgcl_free(gtp_sgcl_result* r) { delete r; }

@@ -245,6 +245,56 @@ int gtp_sgcl_is_normalized(const gtp_sgcl_result* r);
 void gtp_sgcl_probs(const gtp_sgcl_result* r, double* unnormalized, double* normalized); /* p(i), p(i)/Z */
 void gtp_sgcl_stats(const gtp_sgcl_result* r, uint64_t* nodes_evaluated, uint64_t* cache_hits);
 
+/* ---- Interval<F64> TaylorPoly on the device -------------------------------------------------------------
+ * The number type of the reference's --bounds mode: TaylorPoly<Interval<F64>> (src/interval.rs:11-15 with the one-ulp
+ * widening of :29-31 / number/f64.rs:127-171 after every operation).  `gti_poly` mirrors `gtp_poly`: each entry point
+ * replaces the TaylorPoly<T> method of the same name in src/multivariate_taylor.rs at T = Interval<F64> (line numbers as
+ * for the gtp_* functions above).  Coefficients cross the boundary as (lo, hi) pairs of doubles.  Products and the
+ * element-wise family evaluate in the reference's term order; div / exp / log use coefficient-wise recurrences whose
+ * results are valid enclosures a few ulps different from the reference's slice-wise recursion. */
+typedef struct gti_poly gti_poly;
+int gti_from_scalar(gtp_ctx* ctx, double lo, double hi, gti_poly** out);                                  /* :207-215 */
+int gti_zero_with(gtp_ctx* ctx, int ndim, const uint64_t* degrees_p1, gti_poly** out);                    /* :66-72 */
+int gti_var(gtp_ctx* ctx, uint64_t v, double lo, double hi, uint64_t len, gti_poly** out);                /* :239-248 */
+int gti_var_at_zero(gtp_ctx* ctx, uint64_t v, uint64_t len, gti_poly** out);                              /* :228-237 */
+int gti_var_with_degrees_p1(gtp_ctx* ctx, uint64_t v, double lo, double hi, int ndim, const uint64_t* degrees_p1,
+                            gti_poly** out);                                                              /* :250-259 */
+/* data: prod(shape) (lo, hi) pairs when pairs != 0, else prod(shape) doubles taken as point intervals */
+int gti_from_host(gtp_ctx* ctx, int ndim, const uint64_t* shape, const uint64_t* degrees_p1, const double* data, int pairs,
+                  gti_poly** out);                                                                        /* :55-64 */
+int gti_to_host(gtp_ctx* ctx, const gti_poly* p, double* out_pairs);   /* 2 * gti_len(p) doubles */
+void gti_free(gtp_ctx* ctx, gti_poly* p);
+int gti_ndim(const gti_poly* p);
+uint64_t gti_len(const gti_poly* p);
+void gti_shape(const gti_poly* p, uint64_t* out);
+void gti_degrees_p1(const gti_poly* p, uint64_t* out);
+int gti_add(gtp_ctx* ctx, const gti_poly* a, const gti_poly* b, gti_poly** out);                          /* :854-882 */
+int gti_sub(gtp_ctx* ctx, const gti_poly* a, const gti_poly* b, gti_poly** out);                          /* :911-937 */
+int gti_mul(gtp_ctx* ctx, const gti_poly* a, const gti_poly* b, gti_poly** out);                          /* :1014-1072 */
+int gti_div(gtp_ctx* ctx, const gti_poly* a, const gti_poly* b, gti_poly** out);                          /* :1194-1231 */
+int gti_neg(gtp_ctx* ctx, const gti_poly* a, gti_poly** out);                                             /* :902-909 */
+int gti_exp(gtp_ctx* ctx, const gti_poly* a, gti_poly** out);                                             /* :406-417 */
+int gti_log(gtp_ctx* ctx, const gti_poly* a, gti_poly** out);                                             /* :419-430 */
+int gti_pow(gtp_ctx* ctx, const gti_poly* a, uint32_t e, gti_poly** out);                                 /* :433-451 */
+int gti_derivative(gtp_ctx* ctx, const gti_poly* a, uint64_t v, uint64_t n, gti_poly** out);              /* :453-483 */
+int gti_taylor_expansion_of_coeff(gtp_ctx* ctx, const gti_poly* a, uint64_t v, uint64_t n, gti_poly** out); /* :485-512 */
+int gti_shift_down(gtp_ctx* ctx, const gti_poly* a, uint64_t v, uint64_t n, gti_poly** out);              /* :514-536 */
+int gti_coefficients_of_term(gtp_ctx* ctx, const gti_poly* a, uint64_t v, uint64_t order, gti_poly** out); /* :341-358 */
+int gti_taylor_polynomial_terms(gtp_ctx* ctx, const gti_poly* a, uint64_t v, const uint64_t* orders, int n_orders,
+                                gti_poly** out);                                                          /* :380-404 */
+int gti_subst_var(gtp_ctx* ctx, const gti_poly* a, uint64_t v, const gti_poly* subst, gti_poly** out);    /* :538-580 */
+int gti_truncate_to_degree_p1(gtp_ctx* ctx, const gti_poly* a, uint64_t degree_p1, gti_poly** out);       /* :183-193 */
+int gti_remove_last_variable(gtp_ctx* ctx, const gti_poly* a, gti_poly** out);                            /* :172-181 */
+int gti_extend_to_dim(gtp_ctx* ctx, const gti_poly* a, uint64_t ndim, uint64_t degree_p1, gti_poly** out); /* :81-89 */
+int gti_constant_term(gtp_ctx* ctx, const gti_poly* a, double* out2);                                     /* :261-265 */
+int gti_extract_constant(gtp_ctx* ctx, const gti_poly* a, int* is_constant, double* out2);                /* :217-226 */
+int gti_gather_axis(gtp_ctx* ctx, const gti_poly* a, uint64_t v, uint64_t count, double* out_pairs);      /* coefficient() x count */
+/* The host evaluator over gti_*: enclosures of rest mass, total mass Z, raw moments 1..4 (out12: lo, hi pairs) and of
+ * the first `limit` probability masses -- the reference's `run_program::<Interval<F64>>` restricted to its direct outputs
+ * (src/main.rs:150-227).  GenFun constants are the f64 constants of the f64 path as point intervals. */
+int gtp_run_sgcl_bounds(gtp_ctx* ctx, const char* source, int64_t limit, uint64_t unroll, double* out12,
+                        double* probs_lohi, char* err, size_t err_cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,6 +12,7 @@ pub const GTP_UNBOUNDED: u64 = u64::MAX; // usize::MAX on 64-bit targets
 #[repr(C)] pub struct gtp_poly { _p: [u8; 0] }
 #[repr(C)] pub struct gtu_series { _p: [u8; 0] }
 #[repr(C)] pub struct gtp_sgcl_result { _p: [u8; 0] }
+#[repr(C)] pub struct gti_poly { _p: [u8; 0] }
 
 extern "C" {
     // ---- BEGIN GENERATED (tools/gen_rust_externs.py) ----
@@ -111,6 +112,39 @@ extern "C" {
     pub fn gtp_sgcl_is_normalized(r: *const gtp_sgcl_result) -> c_int;
     pub fn gtp_sgcl_probs(r: *const gtp_sgcl_result, unnormalized: *mut f64, normalized: *mut f64);
     pub fn gtp_sgcl_stats(r: *const gtp_sgcl_result, nodes_evaluated: *mut u64, cache_hits: *mut u64);
+    pub fn gti_from_scalar(ctx: *mut gtp_ctx, lo: f64, hi: f64, out: *mut *mut gti_poly) -> c_int;
+    pub fn gti_zero_with(ctx: *mut gtp_ctx, ndim: c_int, degrees_p1: *const u64, out: *mut *mut gti_poly) -> c_int;
+    pub fn gti_var(ctx: *mut gtp_ctx, v: u64, lo: f64, hi: f64, len: u64, out: *mut *mut gti_poly) -> c_int;
+    pub fn gti_var_at_zero(ctx: *mut gtp_ctx, v: u64, len: u64, out: *mut *mut gti_poly) -> c_int;
+    pub fn gti_var_with_degrees_p1(ctx: *mut gtp_ctx, v: u64, lo: f64, hi: f64, ndim: c_int, degrees_p1: *const u64, out: *mut *mut gti_poly) -> c_int;
+    pub fn gti_from_host(ctx: *mut gtp_ctx, ndim: c_int, shape: *const u64, degrees_p1: *const u64, data: *const f64, pairs: c_int, out: *mut *mut gti_poly) -> c_int;
+    pub fn gti_to_host(ctx: *mut gtp_ctx, p: *const gti_poly, out_pairs: *mut f64) -> c_int;
+    pub fn gti_free(ctx: *mut gtp_ctx, p: *mut gti_poly);
+    pub fn gti_ndim(p: *const gti_poly) -> c_int;
+    pub fn gti_len(p: *const gti_poly) -> u64;
+    pub fn gti_shape(p: *const gti_poly, out: *mut u64);
+    pub fn gti_degrees_p1(p: *const gti_poly, out: *mut u64);
+    pub fn gti_add(ctx: *mut gtp_ctx, a: *const gti_poly, b: *const gti_poly, out: *mut *mut gti_poly) -> c_int;
+    pub fn gti_sub(ctx: *mut gtp_ctx, a: *const gti_poly, b: *const gti_poly, out: *mut *mut gti_poly) -> c_int;
+    pub fn gti_mul(ctx: *mut gtp_ctx, a: *const gti_poly, b: *const gti_poly, out: *mut *mut gti_poly) -> c_int;
+    pub fn gti_div(ctx: *mut gtp_ctx, a: *const gti_poly, b: *const gti_poly, out: *mut *mut gti_poly) -> c_int;
+    pub fn gti_neg(ctx: *mut gtp_ctx, a: *const gti_poly, out: *mut *mut gti_poly) -> c_int;
+    pub fn gti_exp(ctx: *mut gtp_ctx, a: *const gti_poly, out: *mut *mut gti_poly) -> c_int;
+    pub fn gti_log(ctx: *mut gtp_ctx, a: *const gti_poly, out: *mut *mut gti_poly) -> c_int;
+    pub fn gti_pow(ctx: *mut gtp_ctx, a: *const gti_poly, e: u32, out: *mut *mut gti_poly) -> c_int;
+    pub fn gti_derivative(ctx: *mut gtp_ctx, a: *const gti_poly, v: u64, n: u64, out: *mut *mut gti_poly) -> c_int;
+    pub fn gti_taylor_expansion_of_coeff(ctx: *mut gtp_ctx, a: *const gti_poly, v: u64, n: u64, out: *mut *mut gti_poly) -> c_int;
+    pub fn gti_shift_down(ctx: *mut gtp_ctx, a: *const gti_poly, v: u64, n: u64, out: *mut *mut gti_poly) -> c_int;
+    pub fn gti_coefficients_of_term(ctx: *mut gtp_ctx, a: *const gti_poly, v: u64, order: u64, out: *mut *mut gti_poly) -> c_int;
+    pub fn gti_taylor_polynomial_terms(ctx: *mut gtp_ctx, a: *const gti_poly, v: u64, orders: *const u64, n_orders: c_int, out: *mut *mut gti_poly) -> c_int;
+    pub fn gti_subst_var(ctx: *mut gtp_ctx, a: *const gti_poly, v: u64, subst: *const gti_poly, out: *mut *mut gti_poly) -> c_int;
+    pub fn gti_truncate_to_degree_p1(ctx: *mut gtp_ctx, a: *const gti_poly, degree_p1: u64, out: *mut *mut gti_poly) -> c_int;
+    pub fn gti_remove_last_variable(ctx: *mut gtp_ctx, a: *const gti_poly, out: *mut *mut gti_poly) -> c_int;
+    pub fn gti_extend_to_dim(ctx: *mut gtp_ctx, a: *const gti_poly, ndim: u64, degree_p1: u64, out: *mut *mut gti_poly) -> c_int;
+    pub fn gti_constant_term(ctx: *mut gtp_ctx, a: *const gti_poly, out2: *mut f64) -> c_int;
+    pub fn gti_extract_constant(ctx: *mut gtp_ctx, a: *const gti_poly, is_constant: *mut c_int, out2: *mut f64) -> c_int;
+    pub fn gti_gather_axis(ctx: *mut gtp_ctx, a: *const gti_poly, v: u64, count: u64, out_pairs: *mut f64) -> c_int;
+    pub fn gtp_run_sgcl_bounds(ctx: *mut gtp_ctx, source: *const c_char, limit: i64, unroll: u64, out12: *mut f64, probs_lohi: *mut f64, err: *mut c_char, err_cap: usize) -> c_int;
     // ---- END GENERATED ----
 }
 

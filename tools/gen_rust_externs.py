@@ -39,7 +39,7 @@ def declarations():
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     text = re.sub(r"#.*", "", text)
     decls = []
-    for m in re.finditer(r"([A-Za-z_][\w \*]*?)\b(gt[pu]_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text):
+    for m in re.finditer(r"([A-Za-z_][\w \*]*?)\b(gt[piu]_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text):
         ret, name, args = m.group(1).strip(), m.group(2), m.group(3).strip()
         params = []
         if args and args != "void":
