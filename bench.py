@@ -209,6 +209,42 @@ def run_sgcl_block(ctx, gpu_reps: int = 5):
     return out
 
 
+def run_bounds_block(ctx):
+    """the interval-enclosure run (host evaluator over TaylorPoly<Interval<F64>>, gti_* kernels) -- wall time through
+    gtp_run_sgcl_bounds, and for one program the oracle's interval instantiation on one host core beside it."""
+    import genfer_b200
+    from genfer_b200.interval import run_sgcl_bounds
+    from oracle import oracle as O
+    out = []
+    for label, rel, limit, with_cpu in (("population_50_3vars --limit 60", "slow/population_50_3vars.sgcl", 60, True),
+                                        ("two_populations2000", "slow/two_populations2000.sgcl", None, False)):
+        path = os.path.join(SGCL_DIR, rel)
+        if not os.path.exists(path):
+            out.append({"program": label, "error": "fixture missing"})
+            continue
+        src = open(path).read()
+        opts = genfer_b200.parse_flags(src)
+        g = genfer_b200.run_sgcl(src, limit=limit if limit is not None else opts["limit"], no_simplify_gf=opts["no_simplify_gf"],
+                                 unroll=opts["unroll"], ctx=ctx)
+        n, tg, launches, b = len(g.probs), [], 0, None
+        for _ in range(3):
+            l0 = ctx.launch_count
+            t = time.perf_counter()
+            b = run_sgcl_bounds(src, limit=n, unroll=opts["unroll"], ctx=ctx)
+            tg.append(time.perf_counter() - t)
+            launches = ctx.launch_count - l0
+        inside = b.total[0] <= g.total <= b.total[1] and all(lo <= p <= hi for p, (lo, hi) in zip(g.probs, b.probs))
+        rec = {"program": label, "gpu_bounds_s": min(tg), "gpu_launches": int(launches), "f64_results_inside": bool(inside),
+               "Z_enclosure": list(b.total)}
+        if with_cpu:
+            t = time.perf_counter()
+            o = O.run_sgcl_bounds(src, limit=n, unroll=opts["unroll"])
+            rec["cpu_oracle_bounds_s"] = time.perf_counter() - t
+            rec["speedup"] = rec["cpu_oracle_bounds_s"] / rec["gpu_bounds_s"]
+            rec["overlaps_oracle"] = bool(max(b.total[0], o.total[0]) <= min(b.total[1], o.total[1]))
+        out.append(rec)
+    return out
+
 
 def host_cores() -> int:
     try:
@@ -529,11 +565,12 @@ def run_ours(args):
         parity["max_rel_err"] = max(parity["max_rel_err"], worst)
         parity["coefficients_checked"] += int(checked)
 
-    sweep, sgcl = None, None
+    sweep, sgcl, bounds = None, None, None
     if rank == 0 and world == 1 and not args.no_sweep:
         sweep = run_sweep(ctx, torch, peak, 0.0 if args.no_cpu else args.cpu_budget_gmac * 0.1)
     if rank == 0 and world == 1 and not args.no_sgcl:
         sgcl = run_sgcl_block(ctx)
+        bounds = run_bounds_block(ctx)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -556,7 +593,7 @@ def run_ours(args):
                 "kernel_ms_max_over_ranks": ms_kernel_max,
                 "first_call": {"ms": first_call_ms, "steady_ms": ms_total / K,
                                "note": "first product of a shape builds + uploads the kernel's step/unit tables (host) and synchronises once"},
-                "sweep": sweep, "sgcl": sgcl}
+                "sweep": sweep, "sgcl": sgcl, "bounds": bounds}
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:
