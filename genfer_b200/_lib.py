@@ -100,6 +100,8 @@ _SIGS = {
     "gtp_sgcl_is_normalized": (C.c_int, [vp]),
     "gtp_sgcl_probs": (None, [vp, f64p, f64p]),
     "gtp_sgcl_stats": (None, [vp, u64p, u64p]),
+    "gtp_sgcl_moment_bounds": (None, [vp, f64p]),
+    "gtp_sgcl_prob_bounds": (None, [vp, f64p, f64p]),
     "gtp_run_sgcl_bounds": (C.c_int, [vp, C.c_char_p, C.c_int64, C.c_uint64, f64p, f64p, C.c_char_p, C.c_size_t]),
     "gti_from_scalar": (C.c_int, [vp, C.c_double, C.c_double, vpp]),
     "gti_zero_with": (C.c_int, [vp, C.c_int, u64p, vpp]),

@@ -95,6 +95,9 @@ struct IvS {
   IvS() = default;
   IvS(double x) : v{x, x} {}
   explicit IvS(gti::Iv i) : v(i) {}
+  static IvS from_bounds(double lo, double hi) { return IvS(gti::iv(lo, hi)); }
+  double lower() const { return v.lo; }
+  double upper() const { return v.hi; }
   friend IvS operator+(const IvS& a, const IvS& b) { return IvS(gti::iv_add(a.v, b.v)); }
   friend IvS operator-(const IvS& a, const IvS& b) { return IvS(gti::iv_sub(a.v, b.v)); }
   friend IvS operator*(const IvS& a, const IvS& b) { return IvS(gti::iv_mul(a.v, b.v)); }
@@ -194,7 +197,6 @@ int gtp_run_sgcl(gtp_ctx* ctx, const char* source, int64_t limit, int flags, uin
                  char* err, size_t err_cap) {
   if (!ctx || !source || !out) return GTP_ERR_ARG;
   try {
-    GpuBackend backend{ctx};
     gfe::RunOptions opt;
     if (limit >= 0) opt.limit = (size_t)limit;
     opt.no_probs = (flags & 1) != 0;
@@ -202,7 +204,13 @@ int gtp_run_sgcl(gtp_ctx* ctx, const char* source, int64_t limit, int flags, uin
     opt.bounds = (flags & 4) != 0;
     opt.unroll = (size_t)unroll;
     auto res = std::make_unique<gtp_sgcl_result>();
-    res->r = gfe::run_program(backend, source, opt);
+    if (opt.bounds) {   // --bounds: run_program_intervals::<F64> (main.rs:145-185) over TaylorPoly<Interval<F64>> on the device
+      GpuIvBackend backend{ctx};
+      res->r = gfe::run_program(backend, source, opt);
+    } else {
+      GpuBackend backend{ctx};
+      res->r = gfe::run_program(backend, source, opt);
+    }
     *out = res.release();
     return GTP_OK;
   } catch (const std::exception& e) {
@@ -215,7 +223,8 @@ int gtp_run_sgcl(gtp_ctx* ctx, const char* source, int64_t limit, int flags, uin
 }
 // The --bounds-style enclosure of the evaluator's direct outputs with the interval arithmetic on the device: the
 // same host logic over TaylorPoly<Interval<F64>> (gti_*).  GenFun constants are the f64 values of the f64 path, as point
-// intervals; no simplification pass (its polynomial form stores f64 coefficients).
+// intervals; no simplification pass (its polynomial form stores f64 coefficients).  Constants that come from a ratio in the
+// program text are the enclosures Number::from_ratio builds (evaluator/num.hpp), so the result encloses the exact posterior.
 // out12: [rest lo, hi, total lo, hi, raw moment 1..4 lo, hi]; probs_lohi: `limit` (lo, hi) pairs (may be null when limit <= 0).
 int gtp_run_sgcl_bounds(gtp_ctx* ctx, const char* source, int64_t limit, uint64_t unroll, double* out12, double* probs_lohi,
                         char* err, size_t err_cap) {
@@ -258,6 +267,20 @@ void gtp_sgcl_probs(const gtp_sgcl_result* r, double* unnormalized, double* norm
   for (size_t i = 0; i < x.probs.size(); i++) {
     if (unnormalized) unnormalized[i] = x.probs[i];
     if (normalized) normalized[i] = x.is_normalized ? x.probs[i] : x.normalized_probs[i];
+  }
+}
+void gtp_sgcl_moment_bounds(const gtp_sgcl_result* r, double* out22) {
+  for (size_t i = 0; i < r->r.moment_bounds.size() && i < 11; i++) {
+    out22[2 * i] = r->r.moment_bounds[i].lo;
+    out22[2 * i + 1] = r->r.moment_bounds[i].hi;
+  }
+}
+void gtp_sgcl_prob_bounds(const gtp_sgcl_result* r, double* unnormalized_pairs, double* normalized_pairs) {
+  const gfe::RunResult& x = r->r;
+  for (size_t i = 0; i < x.prob_bounds.size(); i++) {
+    const gfe::Iv n = x.is_normalized ? x.prob_bounds[i] : x.normalized_prob_bounds[i];
+    if (unnormalized_pairs) { unnormalized_pairs[2 * i] = x.prob_bounds[i].lo; unnormalized_pairs[2 * i + 1] = x.prob_bounds[i].hi; }
+    if (normalized_pairs) { normalized_pairs[2 * i] = n.lo; normalized_pairs[2 * i + 1] = n.hi; }
   }
 }
 void gtp_sgcl_stats(const gtp_sgcl_result* r, uint64_t* nodes_evaluated, uint64_t* cache_hits) {

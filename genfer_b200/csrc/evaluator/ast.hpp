@@ -10,6 +10,8 @@
 #include <string>
 #include <vector>
 
+#include "num.hpp"
+
 namespace gfe {
 
 struct EvalError : std::runtime_error {
@@ -37,6 +39,8 @@ struct PosRatio {  // ppl.rs:33-72
   }
   // Number::from_ratio for F64 (number/f64.rs:49-51): one IEEE division
   double to_f64() const { return (double)numer / (double)denom; }
+  // T::from_ratio under T = F64 and T = Interval<F64> at once (num.hpp)
+  Num to_num() const { return Num::from_ratio(numer, denom); }
 };
 
 enum class DistKind {

@@ -19,12 +19,26 @@ namespace gfe {
 
 constexpr uint64_t UNBOUNDED = UINT64_MAX;
 
+// A GenFun constant as the backend's scalar: its f64 value for T = F64, its enclosure for an interval scalar type (which
+// provides `from_bounds(lo, hi)`, `lower()`, `upper()`).
+template <class S>
+inline S scalar_of(const Num& x) {
+  if constexpr (std::is_same<S, double>::value) return x.v;
+  else return S::from_bounds(x.iv.lo, x.iv.hi);
+}
+template <class S>
+inline Iv bounds_of(const S& x) {
+  if constexpr (std::is_same<S, double>::value) return Iv::precisely(x);   // print_moments_and_probs (main.rs:256-289)
+  else return Iv::exact(x.lower(), x.upper());
+}
+
 template <class B>
 class Evaluator {
  public:
   using Poly = typename B::Poly;
   // The scalar type T of the reference's TaylorPoly<T>: double in the product (GpuBackend) and in the f64 oracle; the
-  // oracle's --bounds instantiation uses Interval<F64>.  GenFun constants stay f64 (they become point intervals).
+  // --bounds instantiations (oracle and gti_* on the device) use Interval<F64>; a GenFun constant then enters as the enclosure
+  // Number::from_ratio builds for it (num.hpp), not as the rounded f64 value.
   using S = typename B::Scalar;
   explicit Evaluator(B& backend) : b_(backend) {}
 
@@ -121,7 +135,7 @@ class Evaluator {
   std::optional<Poly> simplify_node(const GfNode& n) {
     switch (n.kind) {
       case GfNode::Var: return b_.var_with_degrees(n.var, S(0.0), std::vector<uint64_t>(n.var + 1, UNBOUNDED));
-      case GfNode::Const: return b_.from_scalar(S(n.value));
+      case GfNode::Const: return b_.from_scalar(scalar_of<S>(Num(n.value, n.bounds)));
       case GfNode::Add: case GfNode::Mul: case GfNode::Div: {
         auto p1 = simplify_with(n.a);
         auto p2 = simplify_with(n.b);
@@ -179,7 +193,7 @@ class Evaluator {
     const GfNode& n = *g;
     switch (n.kind) {
       case GfNode::Var: return b_.var(n.var, inputs.at(n.var), degree_p1);
-      case GfNode::Const: return b_.from_scalar(S(n.value));
+      case GfNode::Const: return b_.from_scalar(scalar_of<S>(Num(n.value, n.bounds)));
       case GfNode::Add: { Poly x = eval_with(n.a, inputs, degree_p1); Poly y = eval_with(n.b, inputs, degree_p1); return b_.add(x, y); }
       case GfNode::Neg: return b_.neg(eval_with(n.a, inputs, degree_p1));
       case GfNode::Mul: { Poly x = eval_with(n.a, inputs, degree_p1); Poly y = eval_with(n.b, inputs, degree_p1); return b_.mul(x, y); }
@@ -279,42 +293,42 @@ class Evaluator {
       // D^n(G) with D(G)(y) := lambda y G'(y), evaluated at y = e^(-lambda) y; the 1/n! is folded into the loop
       GenFun f = rec.inner;
       for (size_t k = 1; k <= order; k++)
-        f = gf::mul(gf::mul(gf::derive(f, rec.param_var, 1), gf::var(rec.param_var)), gf::constant(rec.scalar / (double)(uint32_t)k));
-      GenFun repl = gf::mul(gf::constant(std::exp(-rec.scalar)), gf::var(rec.param_var));
+        f = gf::mul(gf::mul(gf::derive(f, rec.param_var, 1), gf::var(rec.param_var)), gf::constant(rec.scalar / Num((double)(uint32_t)k)));
+      GenFun repl = gf::mul(gf::constant(exp(-rec.scalar)), gf::var(rec.param_var));
       f = gf::substitute_var(f, rec.param_var, repl);
       return b_.truncate_to_degree_p1(eval_with(f, inputs, degree_p1), degree_p1);
     }
     if (gf::recognize_continuous_poisson_observation(g, v, &rec)) {
       GenFun f = rec.inner;
       for (size_t k = 1; k <= order; k++)
-        f = gf::mul(gf::derive(f, rec.param_var, 1), gf::constant(rec.scalar / (double)(uint32_t)k));
+        f = gf::mul(gf::derive(f, rec.param_var, 1), gf::constant(rec.scalar / Num((double)(uint32_t)k)));
       GenFun repl = gf::sub(gf::var(rec.param_var), gf::constant(rec.scalar));
       f = gf::substitute_var(f, rec.param_var, repl);
       return b_.truncate_to_degree_p1(eval_with(f, inputs, degree_p1), degree_p1);
     }
     if (gf::recognize_negative_binomial_observation(g, v, &rec)) {
-      const double p = rec.scalar;
-      std::vector<double> lahs{1.0};   // row d of the Lah numbers times (1-p)^d / d!
-      const double one_mp = 1.0 - p;
+      const Num p = rec.scalar;
+      std::vector<Num> lahs{Num(1.0)};   // row d of the Lah numbers times (1-p)^d / d!
+      const Num one_mp = Num(1.0) - p;
       for (size_t d = 1; d <= order; d++) {
-        std::vector<double> next;
+        std::vector<Num> next;
         for (size_t i = 0; i <= d; i++) {
-          double l_dm1_i = i < lahs.size() ? lahs[i] : 0.0;
-          double l_dm1_im1 = (1 <= i && i <= lahs.size()) ? lahs[i - 1] : 0.0;
-          next.push_back(one_mp / (double)(uint32_t)d * (l_dm1_i * (double)(uint32_t)(d + i - 1) + l_dm1_im1));
+          Num l_dm1_i = i < lahs.size() ? lahs[i] : Num(0.0);
+          Num l_dm1_im1 = (1 <= i && i <= lahs.size()) ? lahs[i - 1] : Num(0.0);
+          next.push_back(one_mp / Num((double)(uint32_t)d) * (l_dm1_i * Num((double)(uint32_t)(d + i - 1)) + l_dm1_im1));
         }
         lahs = next;
       }
       Poly sum = b_.zero_with(std::vector<uint64_t>(inputs.size(), degree_p1));
       std::vector<S> new_inputs = inputs;
-      new_inputs.at(rec.param_var) = S(p) * inputs[rec.param_var];
+      new_inputs.at(rec.param_var) = scalar_of<S>(p) * inputs[rec.param_var];
       Poly inner_result = eval_with(rec.inner, new_inputs, degree_p1 + order);
       Poly power = b_.from_scalar(S(1.0));
       Poly param_tp = b_.var(rec.param_var, inputs[rec.param_var], degree_p1);
-      Poly p_param = b_.mul(b_.from_scalar(S(p)), param_tp);
-      for (double lah : lahs) {
-        Poly subst = b_.mul(b_.from_scalar(S(p)), b_.var_at_zero(rec.param_var, degree_p1));
-        Poly term = b_.mul(b_.mul(b_.subst_var(inner_result, rec.param_var, subst), power), b_.from_scalar(S(lah)));
+      Poly p_param = b_.mul(b_.from_scalar(scalar_of<S>(p)), param_tp);
+      for (const Num& lah : lahs) {
+        Poly subst = b_.mul(b_.from_scalar(scalar_of<S>(p)), b_.var_at_zero(rec.param_var, degree_p1));
+        Poly term = b_.mul(b_.mul(b_.subst_var(inner_result, rec.param_var, subst), power), b_.from_scalar(scalar_of<S>(lah)));
         sum = b_.add(sum, term);
         power = b_.mul(power, p_param);
         inner_result = b_.derivative(inner_result, rec.param_var, 1);

@@ -25,7 +25,8 @@ struct GfNode {
     TaylorCoeffAtZero, TaylorCoeff, ShiftTaylorAtZero, Max
   } kind;
   gfe::Var var = 0;           // Var / Subst / Derivative / Taylor* / Shift
-  double value = 0.0;         // Const
+  double value = 0.0;         // Const under T = F64
+  Iv bounds;                  // Const under T = Interval<F64> (--bounds): encloses the exact constant, not just `value`
   uint32_t n = 0;             // Pow exponent
   size_t order = 0;           // Derivative / TaylorCoeff(AtZero) / Shift
   std::vector<size_t> orders; // TaylorPolynomial
@@ -39,11 +40,11 @@ struct GfNode {
 namespace gf {
 inline GenFun make(GfNode n) { return std::make_shared<const GfNode>(std::move(n)); }
 inline GenFun var(Var v) { GfNode n; n.kind = GfNode::Var; n.var = v; return make(n); }
-inline GenFun constant(double x) { GfNode n; n.kind = GfNode::Const; n.value = x; return make(n); }
+inline GenFun constant(const Num& x) { GfNode n; n.kind = GfNode::Const; n.value = x.v; n.bounds = x.iv; return make(n); }
 inline GenFun zero() { return constant(0.0); }
 inline GenFun one() { return constant(1.0); }
 inline GenFun from_u32(uint32_t k) { return constant((double)k); }
-inline GenFun from_ratio(PosRatio r) { return constant(r.to_f64()); }
+inline GenFun from_ratio(PosRatio r) { return constant(r.to_num()); }
 inline GenFun bin(GfNode::Kind k, GenFun a, GenFun b) { GfNode n; n.kind = k; n.a = std::move(a); n.b = std::move(b); return make(n); }
 inline GenFun un(GfNode::Kind k, GenFun a) { GfNode n; n.kind = k; n.a = std::move(a); return make(n); }
 inline GenFun add(GenFun a, GenFun b) { return bin(GfNode::Add, a, b); }
@@ -123,7 +124,7 @@ inline size_t used_vars(const GenFun& g) {
   return used_vars_with(g, cache);
 }
 
-struct Recognised { Var param_var; double scalar; GenFun inner; };
+struct Recognised { Var param_var; Num scalar; GenFun inner; };
 // y * exp(lambda * (x - 1)) substituted for y: observation from Poisson(lambda * Y), Y discrete (:840-866)
 inline bool recognize_discrete_poisson_observation(const GenFun& g, Var aux, Recognised* out) {
   if (g->kind != GfNode::Subst) return false;
@@ -132,8 +133,8 @@ inline bool recognize_discrete_poisson_observation(const GenFun& g, Var aux, Rec
   if (r->b->kind != GfNode::Exp) return false;
   const GenFun& e = r->b->a;
   if (e->kind != GfNode::Mul || e->a->kind != GfNode::Const) return false;
-  if (!equal(e->b, sub(var(aux), constant(1.0)))) return false;
-  *out = {g->var, e->a->value, g->a};
+  if (!equal(e->b, sub(var(aux), one()))) return false;
+  *out = {g->var, Num(e->a->value, e->a->bounds), g->a};
   return true;
 }
 // y + lambda * (x - 1): observation from Poisson(lambda * Y), Y continuous (:868-890)
@@ -143,8 +144,8 @@ inline bool recognize_continuous_poisson_observation(const GenFun& g, Var aux, R
   if (r->kind != GfNode::Add || !equal(r->a, var(g->var))) return false;
   const GenFun& m = r->b;
   if (m->kind != GfNode::Mul || m->a->kind != GfNode::Const) return false;
-  if (!equal(m->b, sub(var(aux), constant(1.0)))) return false;
-  *out = {g->var, m->a->value, g->a};
+  if (!equal(m->b, sub(var(aux), one()))) return false;
+  *out = {g->var, Num(m->a->value, m->a->bounds), g->a};
   return true;
 }
 // y * (p / (1 - (1-p) x)): observation from NegBinomial(Y, p) (:892-914)
@@ -154,8 +155,8 @@ inline bool recognize_negative_binomial_observation(const GenFun& g, Var aux, Re
   if (r->kind != GfNode::Mul || !equal(r->a, var(g->var))) return false;
   const GenFun& d = r->b;
   if (d->kind != GfNode::Div || d->a->kind != GfNode::Const) return false;
-  double p = d->a->value;
-  GenFun expected = sub(one(), mul(constant(1.0 - p), var(aux)));
+  const Num p(d->a->value, d->a->bounds);
+  GenFun expected = sub(one(), mul(constant(Num(1.0) - p), var(aux)));   // compared by its f64 value
   if (!equal(d->b, expected)) return false;
   *out = {g->var, p, g->a};
   return true;

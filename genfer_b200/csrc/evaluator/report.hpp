@@ -15,44 +15,6 @@
 
 namespace gfe {
 
-// ---- F64 scalar helpers ---------------------------------------------------------------------------
-inline double next_up(double x) {
-  uint64_t bits;
-  std::memcpy(&bits, &x, 8);
-  if (std::isnan(x) || bits == 0x7ff0000000000000ULL) return x;
-  uint64_t abs = bits & 0x7fffffffffffffffULL, next;
-  if (abs == 0) next = 1;
-  else if (bits == abs) next = bits + 1;
-  else next = bits - 1;
-  double r;
-  std::memcpy(&r, &next, 8);
-  return r;
-}
-inline double next_down(double x) {
-  uint64_t bits;
-  std::memcpy(&bits, &x, 8);
-  if (std::isnan(x) || bits == 0xfff0000000000000ULL) return x;
-  uint64_t abs = bits & 0x7fffffffffffffffULL, next;
-  if (abs == 0) next = 0x8000000000000001ULL;
-  else if (bits == abs) next = bits - 1;
-  else next = bits + 1;
-  double r;
-  std::memcpy(&r, &next, 8);
-  return r;
-}
-inline double powi(double a, uint32_t b) {  // f64::powi = compiler-rt __powidf2 (binary exponentiation)
-  double r = 1.0;
-  while (true) {
-    if (b & 1) r *= a;
-    b /= 2;
-    if (b == 0) break;
-    a *= a;
-  }
-  return r;
-}
-inline double f64_min(double a, double b) { return a < b ? a : b; }   // number/f64.rs:69-75
-inline double f64_max(double a, double b) { return a > b ? a : b; }   // :77-84
-
 // ryu::Buffer::format (pretty::format64 layout rules on the shortest round-trip digits)
 inline std::string fmt_f64(double x) {
   if (std::isnan(x)) return "NaN";
@@ -88,67 +50,6 @@ inline std::string fmt_f64(double x) {
   }
   return out;
 }
-
-// ---- Interval<F64> (src/interval.rs) -------------------------------------------------------------------
-struct Iv {
-  double lo = 0, hi = 0;
-  static Iv exact(double l, double h) { return {l, h}; }
-  static Iv precisely(double x) { return {x, x}; }
-  static Iv widen(double l, double h) { return {next_down(l), next_up(h)}; }
-  static Iv zero() { return {0.0, 0.0}; }
-  static Iv one() { return {1.0, 1.0}; }
-  bool is_zero() const { return lo == 0.0 && hi == 0.0; }
-  bool is_one() const { return lo == 1.0 && hi == 1.0; }
-  bool is_finite() const { return std::isfinite(lo) && std::isfinite(hi); }
-  bool is_nan() const { return std::isnan(lo) || std::isnan(hi); }
-  bool contains(double x) const { return lo <= x && x <= hi; }
-  Iv unite(double x) const { return {f64_min(lo, x), f64_max(hi, x)}; }
-  bool is_point() const { return lo == hi; }
-  double center() const { return (lo + hi) / 2.0; }
-  Iv ensure_lower_bound(double nl) const { return lo < nl ? Iv{nl, hi} : *this; }
-  Iv ensure_upper_bound(double nh) const { return hi > nh ? Iv{lo, nh} : *this; }
-  Iv neg() const { return {-hi, -lo}; }
-  Iv add(const Iv& r) const {
-    if (is_zero()) return r;
-    if (r.is_zero()) return *this;
-    return widen(lo + r.lo, hi + r.hi);
-  }
-  Iv sub(const Iv& r) const { return add(r.neg()); }
-  Iv mul(const Iv& r) const {
-    if ((is_zero() && r.is_finite()) || (is_finite() && r.is_zero())) return zero();
-    if (is_one()) return r;
-    if (r.is_one()) return *this;
-    if (neg().is_one()) return r.neg();
-    if (r.neg().is_one()) return neg();
-    double a = lo * r.lo, b = lo * r.hi, c = hi * r.lo, d = hi * r.hi;
-    return widen(f64_min(f64_min(f64_min(a, b), c), d), f64_max(f64_max(f64_max(a, b), c), d));
-  }
-  Iv div(const Iv& r) const {
-    if (is_nan() || r.is_nan()) return {NAN, NAN};
-    if (is_zero() && !r.is_zero()) return *this;
-    if (r.is_one()) return *this;
-    double l = INFINITY, h = -INFINITY;
-    if (r.contains(0.0)) {
-      if (0.0 <= lo) h = INFINITY; else l = -INFINITY;
-      if (hi <= 0.0) l = -INFINITY; else h = INFINITY;
-    }
-    double a = lo / r.lo, b = lo / r.hi, c = hi / r.lo, d = hi / r.hi;
-    l = f64_min(f64_min(f64_min(f64_min(l, a), b), c), d);
-    h = f64_max(f64_max(f64_max(f64_max(h, a), b), c), d);
-    return widen(l, h);
-  }
-  Iv pow(uint32_t e) const {
-    Iv r = widen(powi(lo, e), powi(hi, e));
-    return contains(0.0) ? r.unite(0.0) : r;
-  }
-  Iv sqrt() const {
-    double l = lo < 0.0 ? 0.0 : std::sqrt(lo);
-    return widen(l, std::sqrt(hi));
-  }
-  // PartialOrd (:236-248)
-  bool lt(const Iv& o) const { return !(lo == o.lo && hi == o.hi) && hi <= o.lo; }
-  bool gt(const Iv& o) const { return !(lo == o.lo && hi == o.hi) && !(hi <= o.lo) && lo >= o.hi; }
-};
 
 inline std::string in_interval(const Iv& iv, bool print_intervals) {  // main.rs:291-299
   if (iv.is_point()) return "= " + fmt_f64(iv.lo);
@@ -207,7 +108,7 @@ struct RunOptions {
   bool no_probs = false;          // --no-probs
   bool no_simplify_gf = false;    // --no-simplify-gf
   size_t unroll = 8;              // --unroll (default 8, main.rs:66-67)
-  bool bounds = false;            // only changes how non-point intervals are printed
+  bool bounds = false;            // --bounds: non-point intervals are printed as such (with an interval backend they are the result)
 };
 
 struct RunResult {
@@ -219,6 +120,8 @@ struct RunResult {
   double tail_unnorm = 0, tail_norm = 0;
   bool is_normalized = true;
   size_t nodes_evaluated = 0, cache_hits = 0;
+  // the intervals behind the values above (points for an f64 run without rest mass): Z, E, raw 2..4, sigma, V, central 3, 4, S, K
+  std::vector<Iv> moment_bounds, prob_bounds, normalized_prob_bounds;
 };
 
 constexpr size_t MAX_PROB_LIMIT = 1000;   // main.rs:30
@@ -233,9 +136,14 @@ RunResult run_program(B& backend, const std::string& source, const RunOptions& o
   GfTranslation tr = transformer.semantics(program);
   os << transformer.warnings;
   Evaluator<B> ev(backend);
-  if (!opt.no_simplify_gf) {
-    tr.gf = ev.simplify(tr.gf);
-    tr.rest = ev.simplify(tr.rest);
+  using S = typename B::Scalar;
+  // The interval instantiations evaluate the unsimplified DAG: GenFun::simplify stores its polynomial forms with f64 coefficients
+  // here.  (The reference simplifies in --bounds mode too; either DAG gives a valid enclosure of the same exact value.)
+  if constexpr (std::is_same<S, double>::value) {
+    if (!opt.no_simplify_gf) {
+      tr.gf = ev.simplify(tr.gf);
+      tr.rest = ev.simplify(tr.rest);
+    }
   }
   const SupportSet var_info = tr.var_info[program.result];
   const SupportSet rest_info = tr.rest_info[program.result];
@@ -243,16 +151,16 @@ RunResult run_program(B& backend, const std::string& source, const RunOptions& o
   os << "Support is a subset of: " << out.support << "\n\nComputing moments...\n";
 
   // ---- print_moments_and_probs_interval (:301-389) ----
-  double rest_val = backend.constant_term(ev.eval(tr.rest, std::vector<double>(tr.var_info.num_vars(), 0.0), 1));
-  Iv rest = Iv::precisely(rest_val).ensure_lower_bound(0.0).ensure_upper_bound(1.0).unite(0.0);
+  S rest_val = backend.constant_term(ev.eval(tr.rest, std::vector<S>(tr.var_info.num_vars(), S(0.0)), 1));
+  Iv rest = bounds_of<S>(rest_val).ensure_lower_bound(0.0).ensure_upper_bound(1.0).unite(0.0);
   auto mom = ev.moments_taylor(tr.gf, program.result, tr.var_info, 5);
-  Iv total = Iv::precisely(mom.first).ensure_lower_bound(0.0).ensure_upper_bound(1.0);
+  Iv total = bounds_of<S>(mom.first).ensure_lower_bound(0.0).ensure_upper_bound(1.0);
   const Iv total_without_rest = total;
   Iv max_rest = Iv::one().sub(total_without_rest);
   rest = rest.ensure_upper_bound(max_rest.hi);
   total = total.add(rest).ensure_upper_bound(1.0);
   std::vector<Iv> moments;
-  for (double m : mom.second) moments.push_back(Iv::precisely(m).ensure_lower_bound(0.0));
+  for (const S& m : mom.second) moments.push_back(bounds_of<S>(m).ensure_lower_bound(0.0));
   {  // rest_info.to_interval() (support.rs:265-289)
     std::optional<Iv> range;
     if (rest_info.kind == SupportSet::Range) range = Iv::exact((double)rest_info.start, rest_info.end ? (double)*rest_info.end : INFINITY);
@@ -292,6 +200,7 @@ RunResult run_program(B& backend, const std::string& source, const RunOptions& o
   out.total = val(total); out.mean = val(mean); out.raw2 = val(raw2); out.raw3 = val(raw3); out.raw4 = val(raw4);
   out.stddev = val(stddev); out.variance = val(variance); out.central3 = val(central3); out.central4 = val(central4);
   out.skewness = val(skewness); out.kurtosis = val(kurtosis);
+  out.moment_bounds = {total, mean, raw2, raw3, raw4, stddev, variance, central3, central4, skewness, kurtosis};
 
   if (!(opt.no_probs || !var_info.is_discrete() || total.is_zero())) {
     // ---- print_probs (:391-473) ----
@@ -315,14 +224,15 @@ RunResult run_program(B& backend, const std::string& source, const RunOptions& o
     os << "Computing probabilities up to " << limit << "...\n";
     const bool is_normalized = !uses_observe || tot.is_one();
     Iv mass_missing = total_without_rest;
-    std::vector<double> raw = ev.probs_taylor(tr.gf, program.result, tr.var_info, limit);
+    std::vector<S> raw = ev.probs_taylor(tr.gf, program.result, tr.var_info, limit);
     for (size_t i = 0; i < limit; i++) {
-      Iv p = Iv::precisely(raw[i]);
+      Iv p = bounds_of<S>(raw[i]);
       mass_missing = mass_missing.sub(p);
       if (rest_info.contains((uint32_t)i)) p = p.add(rest);
       GFE_ASSERT(!(p.lt(Iv::zero()) || p.gt(Iv::one())), "p(" + std::to_string(i) + ") is not a probability");
       p = p.ensure_lower_bound(0.0).ensure_upper_bound(1.0);
       out.probs.push_back(val(p));
+      out.prob_bounds.push_back(p);
       if (is_normalized) {
         os << "p(" << i << ") " << in_interval(p, pi) << "\n";
       } else {
@@ -330,6 +240,7 @@ RunResult run_program(B& backend, const std::string& source, const RunOptions& o
         os << "Unnormalized: p(" << i << ")     " << in_interval(p, pi) << "\n";
         os << "Normalized:   p(" << i << ") / Z " << in_interval(np, pi) << "\n";
         out.normalized_probs.push_back(val(np));
+        out.normalized_prob_bounds.push_back(np);
       }
     }
     SupportSet up_to = SupportSet::range(0, (uint32_t)limit - 1);

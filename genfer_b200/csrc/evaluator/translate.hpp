@@ -21,7 +21,7 @@ struct GfTranslation {
   GfTranslation plus(const GfTranslation& o) const {  // :46-57
     return {var_info.join(o.var_info), gf::add(gf, o.gf), gf::add(rest, o.rest), rest_info.join(o.rest_info)};
   }
-  void scale(double c) {  // :59-64
+  void scale(const Num& c) {  // :59-64
     gf = gf::mul(gf, gf::constant(c));
     rest = gf::mul(rest, gf::constant(c));
   }
@@ -40,27 +40,27 @@ inline GenFun marginalize_all(GenFun g, const VarSupport& vi) {  // :651-657
 }
 
 // Event::recognize_const_prob (ppl.rs:339-365)
-inline std::optional<double> recognize_const_prob(const Event& e) {
+inline std::optional<Num> recognize_const_prob(const Event& e) {
   switch (e.kind) {
     case Event::InSet: case Event::VarComparison: return std::nullopt;
     case Event::DataFromDist:
       if (e.dist.kind == DistKind::Bernoulli) {
-        if (e.data == 0) return e.dist.p.complement().to_f64();
-        if (e.data == 1) return e.dist.p.to_f64();
-        return 0.0;
+        if (e.data == 0) return e.dist.p.complement().to_num();
+        if (e.data == 1) return e.dist.p.to_num();
+        return Num(0.0);
       }
       return std::nullopt;
     case Event::Complement: {
       auto p = recognize_const_prob(*e.children[0]);
       if (!p) return std::nullopt;
-      return 1.0 - *p;
+      return Num(1.0) - *p;
     }
     case Event::Intersection: {
-      double r = 1.0;
+      Num r(1.0);
       for (auto& c : e.children) {
         auto p = recognize_const_prob(*c);
         if (!p) return std::nullopt;
-        r *= *p;
+        r = r * *p;
       }
       return r;
     }
@@ -191,7 +191,7 @@ class GfTransformer {
           GfTranslation t = transform_statements(st.then_, init);
           GfTranslation e = transform_statements(st.else_, init);
           t.scale(*f);
-          e.scale(1.0 - *f);
+          e.scale(Num(1.0) - *f);
           return t.plus(e);
         }
         auto br = transform_event(*st.cond, init);
@@ -317,7 +317,7 @@ class GfTransformer {
         break;
       }
       case DistKind::UniformCont: {
-        double width = d.q.to_f64() - d.p.to_f64();
+        const Num width = d.q.to_num() - d.p.to_num();
         GenFun x = gf::mul(gf::constant(width), gf::var(v));
         GenFun uni = gf::mul(gf::uniform_mgf(x), gf::exp(gf::mul(gf::from_ratio(d.p), gf::var(v))));
         out = gf::mul(uni, base);

@@ -18,7 +18,11 @@ MOMENT_NAMES = ("total", "mean", "raw2", "raw3", "raw4", "stddev", "variance", "
 
 class SgclResult:
     def __init__(self, report: str, moments: List[float], probs: List[float], normalized_probs: List[float],
-                 is_normalized: bool, nodes_evaluated: int, cache_hits: int):
+                 is_normalized: bool, nodes_evaluated: int, cache_hits: int, moment_bounds=None, prob_bounds=None,
+                 normalized_prob_bounds=None):
+        self.moment_bounds = moment_bounds                      # 11 (lo, hi) pairs behind `moments`
+        self.prob_bounds = prob_bounds                          # (lo, hi) of the unnormalised p(i)
+        self.normalized_prob_bounds = normalized_prob_bounds    # (lo, hi) of p(i) / Z
         self.report = report
         self.moments = moments
         for name, value in zip(MOMENT_NAMES, moments):
@@ -33,7 +37,7 @@ class SgclResult:
 def parse_flags(source: str):
     """The `# flags: ...` first-line convention of the reference's test harness (tests/integration.rs:18-33)."""
     first = source.split("\n", 1)[0]
-    opts = {"limit": None, "no_probs": False, "no_simplify_gf": False, "unroll": 8, "unsupported": []}
+    opts = {"limit": None, "no_probs": False, "no_simplify_gf": False, "unroll": 8, "bounds": False, "unsupported": []}
     if "flags:" not in first:
         return opts
     toks = first.split("flags:", 1)[1].split()
@@ -48,19 +52,23 @@ def parse_flags(source: str):
             opts["limit"] = int(toks[i + 1]); i += 1
         elif t in ("--unroll", "-u"):
             opts["unroll"] = int(toks[i + 1]); i += 1
-        else:   # --rational, -s, --precision, --bounds, --big-float: number modes that stay on the reference's CPU code
+        elif t == "--bounds":
+            opts["bounds"] = True
+        else:   # --rational, -s, --precision, --big-float: number modes that stay on the reference's CPU code
             opts["unsupported"].append(t)
         i += 1
     return opts
 
 
 def run_sgcl(source: str, limit: Optional[int] = None, no_probs: bool = False, no_simplify_gf: bool = False,
-             unroll: int = 8, ctx: Optional[Context] = None) -> SgclResult:
+             unroll: int = 8, ctx: Optional[Context] = None, bounds: bool = False) -> SgclResult:
+    """`bounds`: the reference's `--bounds` mode -- the evaluator runs over TaylorPoly<Interval<F64>> on the device (gti_*) and
+    the report prints the enclosures."""
     ctx = ctx or default_context()
     lib = ctx.lib
     h = C.c_void_p()
     err = C.create_string_buffer(2048)
-    flags = (1 if no_probs else 0) | (2 if no_simplify_gf else 0)
+    flags = (1 if no_probs else 0) | (2 if no_simplify_gf else 0) | (4 if bounds else 0)
     rc = lib.gtp_run_sgcl(ctx.h, source.encode(), -1 if limit is None else int(limit), flags, unroll, C.byref(h), err, 2048)
     if rc != 0:
         raise TaylorPanic(rc, err.value.decode())
@@ -72,7 +80,12 @@ def run_sgcl(source: str, limit: Optional[int] = None, no_probs: bool = False, n
         lib.gtp_sgcl_probs(h, p, q)
         nodes, hits = C.c_uint64(), C.c_uint64()
         lib.gtp_sgcl_stats(h, C.byref(nodes), C.byref(hits))
+        mb, pb, qb = (C.c_double * 22)(), (C.c_double * max(2 * n, 2))(), (C.c_double * max(2 * n, 2))()
+        lib.gtp_sgcl_moment_bounds(h, mb)
+        lib.gtp_sgcl_prob_bounds(h, pb, qb)
         return SgclResult(lib.gtp_sgcl_report(h).decode(), list(m), list(p)[:n], list(q)[:n],
-                          bool(lib.gtp_sgcl_is_normalized(h)), int(nodes.value), int(hits.value))
+                          bool(lib.gtp_sgcl_is_normalized(h)), int(nodes.value), int(hits.value),
+                          [(mb[2 * i], mb[2 * i + 1]) for i in range(11)], [(pb[2 * i], pb[2 * i + 1]) for i in range(n)],
+                          [(qb[2 * i], qb[2 * i + 1]) for i in range(n)])
     finally:
         lib.gtp_sgcl_free(h)

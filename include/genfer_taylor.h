@@ -229,7 +229,10 @@ int gtu_eq(gtp_ctx* ctx, const gtu_series* a, const gtu_series* b, int* out);   
  * limit 5) and probability masses (probs_taylor :937-967), post-processing and report (main.rs:301-473).  Every
  * TaylorPoly operation of that pipeline is a gtp_* call on `ctx`, i.e. runs in the CUDA library.
  *   limit  : --limit N, or -1 for the reference's automatic limit (finite support, else Markov's inequality)
- *   flags  : 1 = --no-probs, 2 = --no-simplify-gf, 4 = print non-point intervals as [lo, hi] (--bounds style)
+ *   flags  : 1 = --no-probs, 2 = --no-simplify-gf, 4 = --bounds: run_program_intervals::<F64> (src/main.rs:145-185) -- the
+ *            evaluator runs over TaylorPoly<Interval<F64>> on the device (gti_*), ratio constants are the enclosures
+ *            Number::from_ratio builds (number/number.rs:26-33), the report prints "in [lo, hi]" lines (main.rs:291-299);
+ *            the GenFun is evaluated unsimplified in this mode
  *   unroll : --unroll (reference default 8; only used by `while`)
  * On error (parse error, or anything the reference would panic on) returns GTP_ERR_INDEX and copies the message
  * into `err`.  The report is byte-compatible with the reference's stdout under --no-timing. */
@@ -244,6 +247,10 @@ uint64_t gtp_sgcl_limit(const gtp_sgcl_result* r);          /* number of probabi
 int gtp_sgcl_is_normalized(const gtp_sgcl_result* r);
 void gtp_sgcl_probs(const gtp_sgcl_result* r, double* unnormalized, double* normalized); /* p(i), p(i)/Z */
 void gtp_sgcl_stats(const gtp_sgcl_result* r, uint64_t* nodes_evaluated, uint64_t* cache_hits);
+/* the intervals behind gtp_sgcl_moments (11 lo, hi pairs) and gtp_sgcl_probs (limit pairs each; either may be null):
+ * points for a plain f64 run without rest mass, the enclosures themselves for a --bounds run (flags & 4) */
+void gtp_sgcl_moment_bounds(const gtp_sgcl_result* r, double* out22);
+void gtp_sgcl_prob_bounds(const gtp_sgcl_result* r, double* unnormalized_pairs, double* normalized_pairs);
 
 /* ---- Interval<F64> TaylorPoly on the device -------------------------------------------------------------
  * The number type of the reference's --bounds mode: TaylorPoly<Interval<F64>> (src/interval.rs:11-15 with the one-ulp

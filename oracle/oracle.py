@@ -468,7 +468,9 @@ def mul_rows(x: np.ndarray, y: np.ndarray, rshape: Sequence[int], rows: Sequence
 class SgclResult:
     """Outcome of running an SGCL program end to end (report = the reference's stdout with --no-timing)."""
 
-    def __init__(self, report, moments, probs, normalized_probs):
+    def __init__(self, report, moments, probs, normalized_probs, moment_bounds=None, prob_bounds=None):
+        self.moment_bounds = moment_bounds    # 11 (lo, hi) pairs behind `moments` (--bounds runs: the result proper)
+        self.prob_bounds = prob_bounds        # (lo, hi) of the unnormalised p(i)
         self.report = report
         (self.total, self.mean, self.raw2, self.raw3, self.raw4, self.stddev, self.variance, self.central3,
          self.central4, self.skewness, self.kurtosis) = moments
@@ -478,8 +480,10 @@ class SgclResult:
 
 
 def run_sgcl(source: str, limit: Optional[int] = None, no_probs: bool = False, no_simplify_gf: bool = False,
-             unroll: int = 8) -> SgclResult:
-    """The host evaluator instantiated over the CPU oracle (oracle_eval.cpp): reference-order f64 arithmetic."""
+             unroll: int = 8, bounds: bool = False) -> SgclResult:
+    """The host evaluator instantiated over the CPU oracle (oracle_eval.cpp): reference-order f64 arithmetic, or with
+    `bounds` the reference's `--bounds` mode (TaylorPoly<Interval<F64>>, ratio constants enclosed by Number::from_ratio; the
+    report prints intervals).  The interval mode is unpinned: no reference fixture runs with --bounds."""
     L = lib()
     L.orc_run_sgcl.argtypes = [C.c_char_p, C.c_int64, C.c_int, C.c_uint64, C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]
     L.orc_sgcl_report.restype = C.c_char_p
@@ -491,7 +495,9 @@ def run_sgcl(source: str, limit: Optional[int] = None, no_probs: bool = False, n
     L.orc_sgcl_free.argtypes = [C.c_void_p]
     h = C.c_void_p()
     err = C.create_string_buffer(2048)
-    flags = (1 if no_probs else 0) | (2 if no_simplify_gf else 0)
+    flags = (1 if no_probs else 0) | (2 if no_simplify_gf else 0) | (4 if bounds else 0)
+    L.orc_sgcl_moment_bounds.argtypes = [C.c_void_p, _f64p]
+    L.orc_sgcl_prob_bounds.argtypes = [C.c_void_p, _f64p]
     rc = L.orc_run_sgcl(source.encode(), -1 if limit is None else int(limit), flags, unroll, C.byref(h), err, 2048)
     if rc != 0:
         raise OracleError(err.value.decode())
@@ -501,7 +507,11 @@ def run_sgcl(source: str, limit: Optional[int] = None, no_probs: bool = False, n
         n = int(L.orc_sgcl_limit(h))
         p, q = (C.c_double * max(n, 1))(), (C.c_double * max(n, 1))()
         L.orc_sgcl_probs(h, p, q)
-        return SgclResult(L.orc_sgcl_report(h).decode(), list(m), list(p)[:n], list(q)[:n])
+        mb, pb = (C.c_double * 22)(), (C.c_double * max(2 * n, 2))()
+        L.orc_sgcl_moment_bounds(h, mb)
+        L.orc_sgcl_prob_bounds(h, pb)
+        return SgclResult(L.orc_sgcl_report(h).decode(), list(m), list(p)[:n], list(q)[:n],
+                          [(mb[2 * i], mb[2 * i + 1]) for i in range(11)], [(pb[2 * i], pb[2 * i + 1]) for i in range(n)])
     finally:
         L.orc_sgcl_free(h)
 

@@ -28,6 +28,9 @@ struct IvS {
   IvS() = default;
   IvS(double x) : v{x, x} {}
   explicit IvS(orc::Interval i) : v(i) {}
+  static IvS from_bounds(double lo, double hi) { return IvS(orc::Interval{lo, hi}); }
+  double lower() const { return v.lo; }
+  double upper() const { return v.hi; }
   friend IvS operator+(const IvS& a, const IvS& b) { return IvS(a.v + b.v); }
   friend IvS operator-(const IvS& a, const IvS& b) { return IvS(a.v - b.v); }
   friend IvS operator*(const IvS& a, const IvS& b) { return IvS(a.v * b.v); }
@@ -127,7 +130,6 @@ struct orc_sgcl_result {
 extern "C" {
 int orc_run_sgcl(const char* source, int64_t limit, int flags, uint64_t unroll, orc_sgcl_result** out, char* err, size_t err_cap) {
   try {
-    OracleBackend backend;
     gfe::RunOptions opt;
     if (limit >= 0) opt.limit = (size_t)limit;
     opt.no_probs = (flags & 1) != 0;
@@ -135,7 +137,13 @@ int orc_run_sgcl(const char* source, int64_t limit, int flags, uint64_t unroll, 
     opt.bounds = (flags & 4) != 0;
     opt.unroll = (size_t)unroll;
     auto res = std::make_unique<orc_sgcl_result>();
-    res->r = gfe::run_program(backend, source, opt);
+    if (opt.bounds) {   // run_program_intervals::<F64> (main.rs:145-185)
+      IntervalBackend backend;
+      res->r = gfe::run_program(backend, source, opt);
+    } else {
+      OracleBackend backend;
+      res->r = gfe::run_program(backend, source, opt);
+    }
     *out = res.release();
     return 0;
   } catch (const std::exception& e) {
@@ -184,6 +192,18 @@ void orc_sgcl_moments(const orc_sgcl_result* r, double* out11) {
 }
 void orc_sgcl_stats(const orc_sgcl_result* r, uint64_t* nodes, uint64_t* hits) { *nodes = r->r.nodes_evaluated; *hits = r->r.cache_hits; }
 uint64_t orc_sgcl_limit(const orc_sgcl_result* r) { return r->r.probs.size(); }
+void orc_sgcl_moment_bounds(const orc_sgcl_result* r, double* out22) {
+  for (size_t i = 0; i < r->r.moment_bounds.size() && i < 11; i++) {
+    out22[2 * i] = r->r.moment_bounds[i].lo;
+    out22[2 * i + 1] = r->r.moment_bounds[i].hi;
+  }
+}
+void orc_sgcl_prob_bounds(const orc_sgcl_result* r, double* unnormalized_pairs) {
+  for (size_t i = 0; i < r->r.prob_bounds.size(); i++) {
+    unnormalized_pairs[2 * i] = r->r.prob_bounds[i].lo;
+    unnormalized_pairs[2 * i + 1] = r->r.prob_bounds[i].hi;
+  }
+}
 void orc_sgcl_probs(const orc_sgcl_result* r, double* unnormalized, double* normalized) {
   const gfe::RunResult& x = r->r;
   for (size_t i = 0; i < x.probs.size(); i++) {

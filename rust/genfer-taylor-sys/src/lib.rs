@@ -112,6 +112,8 @@ extern "C" {
     pub fn gtp_sgcl_is_normalized(r: *const gtp_sgcl_result) -> c_int;
     pub fn gtp_sgcl_probs(r: *const gtp_sgcl_result, unnormalized: *mut f64, normalized: *mut f64);
     pub fn gtp_sgcl_stats(r: *const gtp_sgcl_result, nodes_evaluated: *mut u64, cache_hits: *mut u64);
+    pub fn gtp_sgcl_moment_bounds(r: *const gtp_sgcl_result, out22: *mut f64);
+    pub fn gtp_sgcl_prob_bounds(r: *const gtp_sgcl_result, unnormalized_pairs: *mut f64, normalized_pairs: *mut f64);
     pub fn gti_from_scalar(ctx: *mut gtp_ctx, lo: f64, hi: f64, out: *mut *mut gti_poly) -> c_int;
     pub fn gti_zero_with(ctx: *mut gtp_ctx, ndim: c_int, degrees_p1: *const u64, out: *mut *mut gti_poly) -> c_int;
     pub fn gti_var(ctx: *mut gtp_ctx, v: u64, lo: f64, hi: f64, len: u64, out: *mut *mut gti_poly) -> c_int;

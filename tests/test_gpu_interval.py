@@ -242,3 +242,59 @@ def test_device_enclosure_on_baseline_programs(ctx, rel):
                              unroll=opts["unroll"], ctx=ctx)
     b = run_sgcl_bounds(src, limit=len(g.probs), unroll=opts["unroll"], ctx=ctx)
     assert check_inside_enclosure(g, b) > 0
+
+
+def report_skeleton(report):
+    """The report with every number replaced: what must be identical between two --bounds runs whose enclosures differ in ulps."""
+    import re
+    return re.sub(r"-?(?:\d+\.\d+(?:e-?\d+)?|inf|NaN)", "#", report)
+
+
+@pytest.mark.parametrize("rel", bounds_fixtures())
+def test_bounds_report_matches_oracle(ctx, rel):
+    """`--bounds` end to end through gtp_run_sgcl (flags & 4): same report layout as the oracle's interval instantiation, every
+    printed enclosure overlaps the oracle's, and the GPU's own f64 results lie inside it."""
+    import math
+    import genfer_b200
+    from oracle import oracle as O
+    src = open(os.path.join(GOLD, rel)).read()
+    opts = genfer_b200.parse_flags(src)
+    kw = dict(limit=opts["limit"], no_probs=opts["no_probs"], no_simplify_gf=opts["no_simplify_gf"], unroll=opts["unroll"])
+    g = genfer_b200.run_sgcl(src, ctx=ctx, bounds=True, **kw)
+    o = O.run_sgcl(src, bounds=True, **kw)
+    assert report_skeleton(g.report) == report_skeleton(o.report)
+    f = genfer_b200.run_sgcl(src, ctx=ctx, **kw)
+    assert len(g.prob_bounds) == len(o.prob_bounds) == len(f.probs)
+    for name, (glo, ghi), (olo, ohi) in zip(["Z", "E", "raw2", "raw3", "raw4", "sigma", "V", "mu3", "mu4", "S", "K"] + [f"p({i})" for i in range(len(f.probs))],
+                                            g.moment_bounds + g.prob_bounds, o.moment_bounds + o.prob_bounds):
+        if all(math.isfinite(x) for x in (glo, ghi, olo, ohi)):
+            assert max(glo, olo) <= min(ghi, ohi), (name, (glo, ghi), (olo, ohi))
+    for name, value, (lo, hi) in zip(["Z", "E", "raw2", "raw3", "raw4"], f.moments[:5], g.moment_bounds[:5]):
+        if math.isfinite(lo) and math.isfinite(hi) and math.isfinite(value):
+            assert lo <= value <= hi, (name, value, (lo, hi))
+    for i, (p, (lo, hi)) in enumerate(zip(f.probs, g.prob_bounds)):
+        if math.isfinite(lo) and math.isfinite(hi):
+            assert lo <= p <= hi, (i, p, (lo, hi))
+
+
+def test_bounds_mode_encloses_exact_posteriors_on_gpu(ctx):
+    """With ratio constants enclosed (Number::from_ratio) the device's intervals contain the exact posterior: C1's closed form
+    Z = 2 e^-2, p(n) = e^-10 10^n / n! * n 0.2 0.8^(n-1), and Pr[burglary] = 2969983/992160802 of prodigy/burglar_alarm."""
+    import math
+    from decimal import Decimal, getcontext
+    from fractions import Fraction
+    import genfer_b200
+    getcontext().prec = 50
+    src = open(os.path.join(GOLD, "config", "example.sgcl")).read()
+    b = genfer_b200.run_sgcl(src, limit=25, ctx=ctx, bounds=True)
+    lo, hi = b.moment_bounds[0]
+    assert Decimal(lo) <= 2 * Decimal(-2).exp() <= Decimal(hi) and hi - lo < 1e-14
+    e10 = Decimal(-10).exp()
+    for n, (lo, hi) in enumerate(b.prob_bounds):
+        exact = e10 * Decimal(10) ** n / Decimal(math.factorial(n)) * n * Decimal(2) / 10 * (Decimal(8) / 10) ** (n - 1) if n else Decimal(0)
+        assert Decimal(lo) <= exact <= Decimal(hi), (n, lo, exact, hi)
+    src = open(os.path.join(GOLD, "config", "burglar_alarm.sgcl")).read()
+    b = genfer_b200.run_sgcl(src, ctx=ctx, bounds=True)
+    lo, hi = b.normalized_prob_bounds[1]
+    assert Fraction(lo) <= Fraction(2969983, 992160802) <= Fraction(hi) and hi - lo < 1e-15
+    assert "Normalized:   p(1) / Z ∈ [" in b.report

@@ -72,3 +72,44 @@ def test_f64_results_inside_interval_enclosure(rel):
     r = O.run_sgcl(src, limit=opts["limit"], no_probs=opts["no_probs"], no_simplify_gf=opts["no_simplify_gf"], unroll=opts["unroll"])
     b = O.run_sgcl_bounds(src, limit=len(r.probs), unroll=opts["unroll"])
     check_inside_enclosure(r, b)
+
+
+def test_bounds_mode_encloses_exact_posteriors():
+    """`--bounds` (run_program_intervals::<F64>, main.rs:145-185): ratio constants enter as the enclosures Number::from_ratio
+    builds, so the printed intervals contain the EXACT posterior -- checked on the closed form of C1 and the exact rational of
+    prodigy/burglar_alarm.  (Unpinned against the reference: none of its fixtures runs with --bounds.)"""
+    from fractions import Fraction
+    from decimal import Decimal, getcontext
+    getcontext().prec = 50
+    src = open(os.path.join(GOLD, "config", "example.sgcl")).read()
+    b = O.run_sgcl(src, limit=25, bounds=True)
+    z = 2 * Decimal(-2).exp()
+    lo, hi = b.moment_bounds[0]
+    assert Decimal(lo) <= z <= Decimal(hi) and hi - lo < 1e-14
+    lo, hi = b.moment_bounds[1]
+    assert lo <= 9.0 <= hi and hi - lo < 1e-12
+    e10 = Decimal(-10).exp()
+    for n, (lo, hi) in enumerate(b.prob_bounds):
+        exact = e10 * Decimal(10) ** n / Decimal(math_factorial(n)) * n * Decimal(2) / 10 * (Decimal(8) / 10) ** (n - 1) if n else Decimal(0)
+        assert Decimal(lo) <= exact <= Decimal(hi), (n, lo, exact, hi)
+    assert "Z ∈ [" in b.report and "p(1)     ∈ [" in b.report
+    src = open(os.path.join(GOLD, "config", "burglar_alarm.sgcl")).read()
+    b = O.run_sgcl(src, bounds=True)
+    lo, hi = [float(x) for x in b.report.split("Normalized:   p(1) / Z ∈ [")[1].split("]")[0].split(", ")]
+    assert Fraction(lo) <= Fraction(2969983, 992160802) <= Fraction(hi) and hi - lo < 1e-15
+
+
+def math_factorial(n):
+    import math
+    return math.factorial(n)
+
+
+def test_from_ratio_enclosures():
+    """Number::from_ratio for Interval<F64> (number/number.rs:26-33): widened even when the quotient is exact; zero and
+    denominators of one stay points (Interval's shortcuts, interval.rs:199-206)."""
+    src = "X ~ Bernoulli(1/2);\nreturn X;\n"
+    b = O.run_sgcl(src, bounds=True)
+    lo, hi = b.prob_bounds[1]
+    assert lo < 0.5 < hi and hi - lo <= 4 * 2.0 ** -53
+    f = O.run_sgcl(src)
+    assert f.probs[1] == 0.5
