@@ -169,7 +169,7 @@ class SgclBounds:
 
 def run_sgcl_bounds(source: str, limit: int = 0, unroll: int = 8, ctx: Optional[Context] = None) -> SgclBounds:
     """The host evaluator over TaylorPoly<Interval<F64>> with all interval arithmetic on the GPU: the enclosure the
-    reference's ``--bounds`` mode computes for the DAG the f64 path evaluates (f64 constants as point intervals)."""
+    reference's ``--bounds`` mode computes (ratio constants enclosed as Number::from_ratio does; unsimplified GenFun)."""
     ctx = ctx or default_context()
     out = (C.c_double * 12)()
     probs = (C.c_double * max(2 * limit, 2))()

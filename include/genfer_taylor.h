@@ -298,7 +298,7 @@ int gti_extract_constant(gtp_ctx* ctx, const gti_poly* a, int* is_constant, doub
 int gti_gather_axis(gtp_ctx* ctx, const gti_poly* a, uint64_t v, uint64_t count, double* out_pairs);      /* coefficient() x count */
 /* The host evaluator over gti_*: enclosures of rest mass, total mass Z, raw moments 1..4 (out12: lo, hi pairs) and of
  * the first `limit` probability masses -- the reference's `run_program::<Interval<F64>>` restricted to its direct outputs
- * (src/main.rs:150-227).  GenFun constants are the f64 constants of the f64 path as point intervals. */
+ * (src/main.rs:150-227).  Ratio constants are the enclosures Number::from_ratio builds (number/number.rs:26-33). */
 int gtp_run_sgcl_bounds(gtp_ctx* ctx, const char* source, int64_t limit, uint64_t unroll, double* out12,
                         double* probs_lohi, char* err, size_t err_cap);
 

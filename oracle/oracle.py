@@ -528,7 +528,7 @@ class SgclBounds:
 
 def run_sgcl_bounds(source: str, limit: int = 0, unroll: int = 8) -> SgclBounds:
     """The host evaluator instantiated over TaylorPoly<Interval<F64>> (the arithmetic of the reference's --bounds mode,
-    src/interval.rs) on the DAG the f64 path evaluates: GenFun constants are the f64 values, as point intervals; no
+    src/interval.rs) on the DAG the f64 path evaluates: ratio constants are the enclosures Number::from_ratio builds; no
     simplification pass.  PARITY UNPINNED: no reference fixture runs with --bounds."""
     L = lib()
     L.orc_run_sgcl_bounds.argtypes = [C.c_char_p, C.c_int64, C.c_uint64, _f64p, _f64p, C.c_char_p, C.c_size_t]

@@ -156,7 +156,8 @@ int orc_run_sgcl(const char* source, int64_t limit, int flags, uint64_t unroll, 
 }
 // --bounds-style enclosure of the evaluator's direct outputs: the same host logic over TaylorPoly<Interval<F64>>
 // (no simplification pass: its polynomial form stores f64 coefficients).  GenFun constants are the f64 values the f64
-// path uses, taken as point intervals, so this encloses the arithmetic of exactly the DAG the f64 / GPU path evaluates.
+// path uses together with the enclosure Number::from_ratio builds for them (evaluator/num.hpp), so this encloses both the exact
+// posterior and the f64 / GPU evaluation of the DAG.
 // out: [rest lo, hi, total lo, hi, raw moment 1..4 lo, hi ...] (12 doubles); probs: `limit` pairs [lo, hi].
 int orc_run_sgcl_bounds(const char* source, int64_t limit, uint64_t unroll, double* out12, double* probs_lohi, char* err, size_t err_cap) {
   try {
