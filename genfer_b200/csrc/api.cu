@@ -983,6 +983,8 @@ int gtp_ctx_create(int device, void* cuda_stream, gtp_ctx** out) {
     return rc;
   }
   if (const char* fm = getenv("GTP_FAST_MUL")) gtp_ctx_set_fast_mul(c, atoi(fm));   // A/B measurements of whole programs
+  if (const char* dc = getenv("GTP_DIRECT_CTAS")) c->direct_ctas = std::max(1, atoi(dc));
+  if (const char* dm = getenv("GTP_DIRECT_MIN")) c->direct_min = (u64)std::max(1ll, atoll(dm));
   *out = c;
   return GTP_OK;
 }
@@ -1028,6 +1030,8 @@ int gtp_ctx_set_fast_mul(gtp_ctx* c, int enabled) {
   c->use_pad = (enabled & 8192) == 0;
   c->use_bulk = (enabled & 16384) == 0;
   c->bulk_products = (enabled & 32768) != 0;
+  c->use_direct = (enabled & 65536) == 0;
+  c->direct_products = (enabled & 131072) != 0;
   c->stencil_v4 = (enabled & 512) == 0;
   c->slide_tile = ((enabled >> 5) & 3) == 1 ? 4 : (((enabled >> 5) & 3) == 2 ? 8 : 0);   // A/B measurements
   enabled &= 3;

@@ -218,6 +218,10 @@ struct Ctx {
   std::shared_ptr<void> slide_plans; // same for kernels_mul_slide.cu
   std::shared_ptr<void> wave_tables; // level tables of the device-resident recurrences (kernels_wave.cu)
   bool bulk_products = false;        // also run plain small-operand products on the row-staged kernel (A/B; slower than the gather kernel)
+  bool use_direct = true;            // row-walking plain-load variant of the Horner step (k_horner_direct), tried before the bulk-copy one
+  bool direct_products = false;      // plain small-operand products on k_horner_direct (A/B: the four-coefficient gather kernel is faster there)
+  u64 direct_min = 1u << 17;         // smallest final tensor (coefficients) that goes to k_horner_direct (GTP_DIRECT_MIN)
+  int direct_ctas = 4;               // resident CTAs per SM for HBM-sized k_horner_direct launches (GTP_DIRECT_CTAS)
   bool use_bulk = true;              // row-staged (bulk-copy / TMA) variant of the Horner step and the small-operand product (A/B tests)
   bool use_pad = true;               // zero-extend odd-shaped dense products to the DFMA kernels' extents (A/B tests)
   bool use_axis = true;              // 1-d operand x N-d tensor: batched axis convolution kernel (false: reference-order kernel; A/B tests)

@@ -414,6 +414,212 @@ __global__ void __launch_bounds__(HB_T) k_horner_rows(const __grid_constant__ Ho
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Row-walking variant with plain coalesced loads.  A warp takes whole rows of the last effective axis (or 32 / W short rows
+// at once, W = the row length rounded up to a power of two): the N-D index, the validity of every group of terms and the
+// source offset of every term are computed ONCE PER ROW, so the element loop is NT back-to-back `ld.global.cg` (coalesced
+// along the row, shifted re-reads of the same row are L2 hits), the reference-order multiply / add chain and one store --
+// no integer division between loads, which is what keeps the per-coefficient gathers (k_horner, k_mul_stencil_v4) latency-
+// bound at 45 % of HBM, and no staging ring whose small bulk copies complete too slowly (k_horner_rows as a single product).
+// Arithmetic per coefficient and its order are k_horner's.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int HD_T = 256;
+struct HornerDirectP {
+  HornerP h;
+  int add_mode;   // 0: product only, 1: Add general path, 2: Add scalar path
+};
+
+template <int NT, int U>
+__global__ void __launch_bounds__(HD_T, (NT <= 4 ? 3 : (NT <= 8 ? 2 : 1))) k_horner_direct(const __grid_constant__ HornerDirectP dp) {
+  const HornerP& p = dp.h;
+  const int ne = p.ne;
+  // step-constant extents and strides live in shared memory (they would cost ~50 registers as unrolled arrays)
+  __shared__ unsigned s_cur[HN_MAXE], s_nxt[HN_MAXE], s_prodsh[HN_MAXE];
+  __shared__ long long s_cstr[HN_MAXE];
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned warps_total = gridDim.x * (HD_T / 32), gw = blockIdx.x * (HD_T / 32) + (threadIdx.x >> 5);
+  double sv[NT];
+#pragma unroll
+  for (int t = 0; t < NT; t++) sv[t] = t < p.nt ? p.subst[p.sidx[t]] : 0.0;
+  if (threadIdx.x == 0)
+    for (int a = 0; a < HN_MAXE; a++) s_nxt[a] = a < ne ? p.shape0[a] : 1u;
+  unsigned phase = 0;
+  const double* src = p.res0;
+  for (unsigned step = 0; step < p.nsteps; step++) {
+    double* dst = p.buf[step & 1u];
+    const unsigned i = p.i_top - step;
+    __syncthreads();
+    if (threadIdx.x < HN_MAXE) {   // one lane per axis; the strides are a suffix product over the lanes
+      const int a = (int)threadIdx.x;
+      const unsigned ca = s_nxt[a];   // the previous step's result shape
+      unsigned pa = 1u, na = 1u;
+      if (a < ne) {
+        const unsigned long long s = (unsigned long long)ca + p.sshape[a] - 1ull;
+        pa = (unsigned)min(s, (unsigned long long)p.d[a]);
+        na = dp.add_mode ? max(pa, p.slice[a]) : pa;
+      }
+      long long st = 1;
+#pragma unroll
+      for (int b = HN_MAXE - 1; b >= 1; --b) {
+        const unsigned cb = __shfl_sync(0xffu, ca, b);
+        if (b > a && b < ne) st *= (long long)cb;
+      }
+      s_cur[a] = ca;
+      s_prodsh[a] = pa;
+      s_nxt[a] = na;
+      s_cstr[a] = a < ne ? st : 0;
+    }
+    __syncthreads();
+    unsigned rows = 1;
+    for (int a = 0; a < ne - 1; a++) rows *= s_nxt[a];
+    const unsigned L_src = s_cur[ne - 1], L_out = s_nxt[ne - 1], L_prod = s_prodsh[ne - 1], L_slice = p.slice[ne - 1];
+    unsigned W = 32;                       // lanes per row
+    while (W > 1 && (W >> 1) >= L_out) W >>= 1;
+    const unsigned G = 32u / W, sub = lane / W, c0 = lane & (W - 1u);
+    const unsigned n_items = (rows + G - 1) / G;
+    const double* slice_base = p.self + (long long)i * p.self_vstr;
+    const long long slice_cstr = p.selfstr[ne - 1];
+    for (unsigned item = gw; item < n_items; item += warps_total) {
+      const unsigned row = item * G + sub;
+      if (row >= rows) continue;
+      // ---- once per row: index, validity of the groups, source offsets of the terms ----
+      bool in_prod = true, in_slice = true;
+      long long so = 0;
+      long long toff[NT];
+      unsigned openmask = (p.nt >= 32) ? 0xffffffffu : ((1u << p.nt) - 1u);
+#pragma unroll
+      for (int t = 0; t < NT; t++) toff[t] = -(long long)p.m[t][ne - 1];
+      {
+        unsigned rem = row;
+        for (int a = ne - 2; a >= 0; --a) {
+          const unsigned na = s_nxt[a], ca = s_cur[a];
+          const long long sa = s_cstr[a];
+          const unsigned q = rem / na, ka = rem - q * na;
+          rem = q;
+          in_prod = in_prod && ka < s_prodsh[a];
+          in_slice = in_slice && ka < p.slice[a];
+          so += (long long)ka * p.selfstr[a];
+#pragma unroll
+          for (int t = 0; t < NT; t++) {
+            const unsigned idx = ka - (unsigned)p.m[t][a];
+            if (idx >= ca) openmask &= ~(1u << t);
+            toff[t] += (long long)idx * sa;
+          }
+        }
+      }
+      double* drow = dst + (size_t)row * L_out;
+      // ---- the row: U chunks per trip, every load of all chunks issued before the first use ----
+      // product of one coefficient in the reference's order; val(t) yields res[k - m_t] (only asked for in-range terms)
+      auto product = [&](unsigned cu, auto&& val) -> double {
+        double total_v = 0.0, inner = 0.0;
+        bool open = false;
+#pragma unroll
+        for (int t = 0; t < NT; t++) {
+          if (t < p.nt) {
+            if (p.group_start[t]) {
+              if (open) total_v = __dadd_rn(total_v, inner);
+              inner = 0.0;
+              open = (openmask >> t) & 1u;
+            }
+            const unsigned cc = cu - (unsigned)p.m[t][ne - 1];
+            if (open && cc < L_src) inner = __dadd_rn(inner, __dmul_rn(val(t), sv[t]));
+          }
+        }
+        if (open) total_v = __dadd_rn(total_v, inner);
+        return total_v;
+      };
+      auto finish = [&](unsigned cu, bool a_ok, double prod, double slv) {
+        double rv;
+        if (dp.add_mode == 0) rv = prod;
+        else if (dp.add_mode == 2) rv = (row == 0 && cu == 0) ? __dadd_rn(prod, slice_base[0]) : prod;
+        else {
+          rv = 0.0;
+          if (a_ok) rv = __dadd_rn(rv, prod);
+          if (in_slice && cu < L_slice) rv = __dadd_rn(rv, slv);
+        }
+        drow[cu] = rv;
+      };
+      {
+        for (unsigned base = 0; base < L_out; base += U * W) {
+          const unsigned c = base + c0;
+          double xv[U][NT], sl[U];
+#pragma unroll
+          for (int u = 0; u < U; u++) {
+            const unsigned cu = c + u * W;
+            const bool a_ok = in_prod && cu < L_prod;
+#pragma unroll
+            for (int t = 0; t < NT; t++) {
+              const unsigned cc = cu - (unsigned)p.m[t][ne - 1];
+              const bool ld = a_ok && ((openmask >> t) & 1u) && cc < L_src;   // out-of-range terms of an absent group are never used
+              xv[u][t] = ld ? ldcg(src + (toff[t] + (long long)cu)) : 0.0;
+            }
+            sl[u] = (dp.add_mode == 1 && in_slice && cu < L_slice) ? slice_base[so + (long long)cu * slice_cstr] : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < U; u++) {
+            const unsigned cu = c + u * W;
+            if (cu >= L_out) continue;
+            const bool a_ok = in_prod && cu < L_prod;
+            const double prod = a_ok ? product(cu, [&](int t) { return xv[u][t]; }) : 0.0;
+            finish(cu, a_ok, prod, sl[u]);
+          }
+        }
+      }
+    }
+    src = dst;
+    if (step + 1 < p.nsteps) grid_barrier(p.bar, phase);
+  }
+}
+
+static bool launch_direct_variant(Ctx& ctx, const HornerP& p, int add_mode, const unsigned* final_shape, u64 final_total, const char* tag) {
+  if (!ctx.use_direct || p.ne < 2) return false;
+  const unsigned L_final = final_shape[p.ne - 1];
+  if (L_final < 48 || final_total < ctx.direct_min) return false;   // short rows: the per-row setup dominates
+  HornerDirectP dp;
+  memset(&dp, 0, sizeof(dp));
+  dp.h = p;
+  dp.add_mode = add_mode;
+  static int coop[64] = {};
+  int& c = coop[ctx.device & 63];
+  if (c == 0) {
+    int vv = 0;
+    cudaDeviceGetAttribute(&vv, cudaDevAttrCooperativeLaunch, ctx.device);
+    c = vv ? 1 : -1;
+  }
+  if (c < 0) return false;
+  const void* fn;
+  int bucket;
+  if (p.nt <= 2) { fn = (const void*)k_horner_direct<2, 4>; bucket = 0; }
+  else if (p.nt <= 4) { fn = (const void*)k_horner_direct<4, 2>; bucket = 1; }
+  else if (p.nt <= 8) { fn = (const void*)k_horner_direct<8, 2>; bucket = 2; }
+  else if (p.nt <= 16) { fn = (const void*)k_horner_direct<16, 1>; bucket = 3; }
+  else { fn = (const void*)k_horner_direct<32, 1>; bucket = 4; }
+  static int per_sm_cached[10][64] = {};
+  int& per_sm = per_sm_cached[bucket][ctx.device & 63];
+  if (per_sm == 0) {
+    GTP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, HD_T, 0));
+    if (per_sm < 1) per_sm = -1;
+  }
+  if (per_sm < 0) return false;
+  // rows per warp item at the final shape; mid-size tensors are barrier-bound (fewer CTAs), HBM-sized ones want loads in flight
+  unsigned W = 32;
+  while (W > 1 && (W >> 1) >= L_final) W >>= 1;
+  const u64 items = (final_total / L_final + (32 / W) - 1) / (32 / W);
+  const int want_per_sm = final_total >= (1u << 21) ? ctx.direct_ctas : (final_total >= (1u << 18) ? 2 : 1);
+  const int ctas_per_sm = std::max(1, std::min(per_sm, want_per_sm));
+  const unsigned grid = (unsigned)std::max<u64>(1, std::min<u64>((items + HD_T / 32 - 1) / (HD_T / 32), (u64)ctas_per_sm * ctx.sm_count));
+  void* args[] = {(void*)&dp};
+  const double t0 = ctx.hist ? Ctx::now() : 0.0;
+  GTP_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(HD_T), args, 0, ctx.stream));
+  ctx.launches++;
+  if (ctx.hist) {
+    (*ctx.hist)[tag]++;
+    ctx.t_launch += Ctx::now() - t0;
+  }
+  return true;
+}
+
 // Fills the group tables from the (sorted) terms of `p` and launches k_horner_rows; false: outside its domain.
 static bool launch_rows_variant(Ctx& ctx, const HornerP& p, int add_mode, const unsigned* final_shape, u64 final_total, const char* tag) {
   if (!ctx.use_bulk || p.ne < 2) return false;
@@ -585,6 +791,7 @@ bool launch_horner(Ctx& ctx, const double* self, const Shape& self_shape, u64 v,
   {
     unsigned fs[HN_MAXE];
     for (int e = 0; e < ne; e++) fs[e] = (unsigned)cur[eff[e]];
+    if (launch_direct_variant(ctx, p, p.slice_scalar ? 2 : 1, fs, final_total, "k_horner_direct")) return true;
     if (launch_rows_variant(ctx, p, p.slice_scalar ? 2 : 1, fs, final_total, "k_horner_rows")) return true;
   }
   static int coop[64] = {};
@@ -690,10 +897,9 @@ bool launch_stencil_rows(Ctx& ctx, const MulArgs& a) {
   p.buf[0] = p.buf[1] = a.out;
   p.i_top = 0;
   p.nsteps = 1;
-  BufP bar = ctx.alloc(2);
-  GTP_CUDA(cudaMemsetAsync(bar->d, 0, 16, ctx.stream));
-  p.bar = reinterpret_cast<unsigned*>(bar->d);
-  return launch_rows_variant(ctx, p, 0, fs, total, "k_horner_rows<product>");
+  p.bar = nullptr;   // a single step never reaches the grid barrier
+  if (ctx.direct_products && launch_direct_variant(ctx, p, 0, fs, total, "k_horner_direct<product>")) return true;
+  return ctx.bulk_products && launch_rows_variant(ctx, p, 0, fs, total, "k_horner_rows<product>");
 }
 
 }  // namespace gtp

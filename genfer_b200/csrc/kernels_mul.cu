@@ -398,7 +398,7 @@ static bool launch_mul_stencil(Ctx& ctx, const MulArgs& a) {
   // The row-staged bulk-copy kernel (kernels_horner.cu) wins inside the fused Horner loop (0.138 s against 0.202 s on
   // population_50_3vars --limit 300) but not on a single product, where the four-coefficient gather below is 2x faster
   // (0.139 ms against 0.269 ms on [297,282,297] x [2,1,2], profiles/r02_stencil_ab.txt): opt-in for A/B measurements.
-  if (ctx.bulk_products && launch_stencil_rows(ctx, a)) return true;
+  if ((ctx.bulk_products || ctx.direct_products) && launch_stencil_rows(ctx, a)) return true;
   StencilP p;
   memset(&p, 0, sizeof(p));
   Shape sst(nd, 1), bst(nd, 1);

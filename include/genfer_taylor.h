@@ -77,8 +77,10 @@ uint64_t gtp_ctx_launch_count(gtp_ctx* ctx);
  * recurrences off (host loops of product launches), +2048 fused Horner loop of subst_var off (three launches per step),
  * +4096 axis-convolution kernel (1-d operand x N-d tensor) off, +8192 zero-extension of odd-shaped dense products to the DFMA
  * kernels' extents off, +16384 row-staged bulk-copy (TMA) variant of the Horner loop off,
- * +32768 plain small-operand products on the row-staged kernel too (slower than the gather kernel; A/B).
- * Environment (read at gtp_ctx_create): GTP_LAUNCH_HIST=1 prints per-kernel launch counts and host-time shares when the
+ * +32768 plain small-operand products on the row-staged kernel too (slower than the gather kernel; A/B),
+ * +65536 row-walking plain-load variant of the Horner loop (k_horner_direct, the default for tensors from 2^17 coefficients
+ * with rows of at least 48) off, +131072 plain small-operand products on that kernel too (A/B).
+ * Environment (read at gtp_ctx_create): GTP_DIRECT_MIN / GTP_DIRECT_CTAS tune k_horner_direct's size threshold and CTAs per SM; GTP_LAUNCH_HIST=1 prints per-kernel launch counts and host-time shares when the
  * context is destroyed; GTP_NO_SCALAR_POOL=1 / GTP_NO_FUSED_CLS=1 switch the host-written scalar slots / the fused
  * classification off. */
 int gtp_ctx_set_fast_mul(gtp_ctx* ctx, int enabled);

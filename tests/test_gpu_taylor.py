@@ -6,6 +6,8 @@ the element-wise/gather family, the reference-order product kernel and the singl
 within 1e-12 relative (north_star) wherever the summation order or libm differs (exp/log, the
 register-tiled product, general division).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -393,12 +395,39 @@ def test_fused_horner_is_bit_exact(G, shape, deg, v, sshape):
     launches = ctx.launch_count - l0
     assert_same(got, o.subst_var(v, os_))
     assert launches <= 12, launches            # a few per-operator steps until res is non-scalar, then ONE kernel
-    # A/B: the per-operator path gives the same bits
-    ctx.set_fast_mul(1 + 2048)
+    # A/B: the per-operator path and the other two fused kernels (row-staged bulk copies; one thread per coefficient) give the same bits
     try:
-        assert_same(g.subst_var(v, gs), o.subst_var(v, os_))
+        for mode in (1 + 2048, 1 + 65536, 1 + 65536 + 16384):
+            ctx.set_fast_mul(mode)
+            assert_same(g.subst_var(v, gs), o.subst_var(v, os_))
     finally:
         ctx.set_fast_mul(1)
+
+
+def test_row_walking_horner_kernel_on_every_case():
+    """k_horner_direct is the default from 2^17 coefficients with rows of at least 48; here every Horner case that has such rows
+    is forced onto it (GTP_DIRECT_MIN=1, read when the context is created), including short first steps (several rows per warp)."""
+    import genfer_b200
+    from oracle import oracle as O
+    old = os.environ.get("GTP_DIRECT_MIN")
+    os.environ["GTP_DIRECT_MIN"] = "1"
+    try:
+        ctx = genfer_b200.Context(0)
+    finally:
+        if old is None:
+            del os.environ["GTP_DIRECT_MIN"]
+        else:
+            os.environ["GTP_DIRECT_MIN"] = old
+    try:
+        cases = HORNER_CASES + [((60, 3, 50), (70, 4, 64), 0, (2, 2, 2)), ((100, 49), (120, 80), 1, (3, 2)), ((4, 200), (6, 260), 0, (2, 3))]
+        for shape, deg, v, sshape in cases:
+            rng = np.random.default_rng(sum(shape) * 7 + v)
+            a, sub = rng.standard_normal(shape), rng.standard_normal(sshape)
+            g, gs = genfer_b200.TaylorPoly.new(a, deg, ctx), genfer_b200.TaylorPoly.new(sub, deg, ctx)
+            o, os_ = O.TaylorPoly.new(a, deg), O.TaylorPoly.new(sub, deg)
+            assert_same(g.subst_var(v, gs), o.subst_var(v, os_))
+    finally:
+        ctx.close()
 
 
 def test_fused_horner_with_zero_slices_and_scalar_slices(G):
