@@ -86,6 +86,31 @@ struct GpuBackend {
     check(gtp_to_host(ctx, a->p, out.data()));
     return out;
   }
+
+  // ---- TaylorExpansion<F64> (univariate_taylor.rs) for the symbolic mode: gtu_* -----------------------------------
+  struct UniHandle {
+    gtp_ctx* c;
+    gtu_series* s;
+    UniHandle(gtp_ctx* c_, gtu_series* s_) : c(c_), s(s_) {}
+    ~UniHandle() { if (s) gtu_free(c, s); }
+    UniHandle(const UniHandle&) = delete;
+    UniHandle& operator=(const UniHandle&) = delete;
+  };
+  using Uni = std::shared_ptr<UniHandle>;
+  Uni uwrap(gtu_series* s) const { return std::make_shared<UniHandle>(ctx, s); }
+  Uni uni_constant(double x) { gtu_series* o; check(gtu_constant(ctx, x, &o)); return uwrap(o); }
+  Uni uni_var(double x, size_t order) { gtu_series* o; check(gtu_var(ctx, x, order, &o)); return uwrap(o); }
+#define GFE_UBIN(name, fn) Uni name(const Uni& a, const Uni& b) { gtu_series* o; check(fn(ctx, a->s, b->s, &o)); return uwrap(o); }
+  GFE_UBIN(uni_add, gtu_add) GFE_UBIN(uni_mul, gtu_mul) GFE_UBIN(uni_div, gtu_div)
+#undef GFE_UBIN
+  Uni uni_exp(const Uni& a) { gtu_series* o; check(gtu_exp(ctx, a->s, &o)); return uwrap(o); }
+  Uni uni_log(const Uni& a) { gtu_series* o; check(gtu_log(ctx, a->s, &o)); return uwrap(o); }
+  Uni uni_pow(const Uni& a, uint32_t e) { gtu_series* o; check(gtu_pow(ctx, a->s, e, &o)); return uwrap(o); }
+  Uni uni_max(const Uni& a, const Uni& b) {   // :219-224: constants only
+    if (!gtu_is_constant(a->s) || !gtu_is_constant(b->s)) throw gfe::EvalError("Maximum can only be applied to constant Taylor expansions.");
+    return uni_constant(scalar_max(uni_coeff(a, 0), uni_coeff(b, 0)));
+  }
+  double uni_coeff(const Uni& a, size_t order) { double x; check(gtu_coeff(ctx, a->s, order, &x)); return x; }
 };
 
 // Interval<F64> as the evaluator sees it (src/interval.rs): constructible from an f64 constant (a point interval); the
@@ -202,6 +227,7 @@ int gtp_run_sgcl(gtp_ctx* ctx, const char* source, int64_t limit, int flags, uin
     opt.no_probs = (flags & 1) != 0;
     opt.no_simplify_gf = (flags & 2) != 0;
     opt.bounds = (flags & 4) != 0;
+    opt.symbolic = (flags & 8) != 0;
     opt.unroll = (size_t)unroll;
     auto res = std::make_unique<gtp_sgcl_result>();
     if (opt.bounds) {   // --bounds: run_program_intervals::<F64> (main.rs:145-185) over TaylorPoly<Interval<F64>> on the device

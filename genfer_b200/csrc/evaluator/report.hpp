@@ -11,6 +11,7 @@
 
 #include "eval.hpp"
 #include "parser.hpp"
+#include "symbolic.hpp"
 #include "translate.hpp"
 
 namespace gfe {
@@ -108,6 +109,7 @@ struct RunOptions {
   bool no_probs = false;          // --no-probs
   bool no_simplify_gf = false;    // --no-simplify-gf
   size_t unroll = 8;              // --unroll (default 8, main.rs:66-67)
+  bool symbolic = false;          // -s: one symbolic computation DAG evaluated over univariate Taylor expansions (symbolic.hpp)
   bool bounds = false;            // --bounds: non-point intervals are printed as such (with an interval backend they are the result)
 };
 
@@ -151,9 +153,26 @@ RunResult run_program(B& backend, const std::string& source, const RunOptions& o
   os << "Support is a subset of: " << out.support << "\n\nComputing moments...\n";
 
   // ---- print_moments_and_probs_interval (:301-389) ----
-  S rest_val = backend.constant_term(ev.eval(tr.rest, std::vector<S>(tr.var_info.num_vars(), S(0.0)), 1));
+  S rest_val;
+  std::pair<S, std::vector<S>> mom;
+  Sym sym_gf;
+  if constexpr (std::is_same<S, double>::value) {
+    if (opt.symbolic) {   // run_program (:196-209): gf.to_computation(), rest.to_computation().evaluate_closed()
+      sym_gf = sym::to_computation(tr.gf);
+      Sym sym_rest = sym::to_computation(tr.rest);
+      SymEvaluator<B> sev(backend);
+      rest_val = sev.closed(sym_rest);
+      mom = sev.moments(sym_gf, program.result, tr.var_info, 5);
+      out.nodes_evaluated += sev.nodes_evaluated;
+    }
+  } else {
+    GFE_ASSERT(!opt.symbolic, "symbolic mode runs over F64 only");
+  }
+  if (!opt.symbolic) {
+    rest_val = backend.constant_term(ev.eval(tr.rest, std::vector<S>(tr.var_info.num_vars(), S(0.0)), 1));
+    mom = ev.moments_taylor(tr.gf, program.result, tr.var_info, 5);
+  }
   Iv rest = bounds_of<S>(rest_val).ensure_lower_bound(0.0).ensure_upper_bound(1.0).unite(0.0);
-  auto mom = ev.moments_taylor(tr.gf, program.result, tr.var_info, 5);
   Iv total = bounds_of<S>(mom.first).ensure_lower_bound(0.0).ensure_upper_bound(1.0);
   const Iv total_without_rest = total;
   Iv max_rest = Iv::one().sub(total_without_rest);
@@ -224,7 +243,15 @@ RunResult run_program(B& backend, const std::string& source, const RunOptions& o
     os << "Computing probabilities up to " << limit << "...\n";
     const bool is_normalized = !uses_observe || tot.is_one();
     Iv mass_missing = total_without_rest;
-    std::vector<S> raw = ev.probs_taylor(tr.gf, program.result, tr.var_info, limit);
+    std::vector<S> raw;
+    if constexpr (std::is_same<S, double>::value) {
+      if (opt.symbolic) {
+        SymEvaluator<B> sev(backend);
+        raw = sev.probs(sym_gf, program.result, tr.var_info, limit);
+        out.nodes_evaluated += sev.nodes_evaluated;
+      }
+    }
+    if (!opt.symbolic) raw = ev.probs_taylor(tr.gf, program.result, tr.var_info, limit);
     for (size_t i = 0; i < limit; i++) {
       Iv p = bounds_of<S>(raw[i]);
       mass_missing = mass_missing.sub(p);
@@ -260,7 +287,7 @@ RunResult run_program(B& backend, const std::string& source, const RunOptions& o
     out.is_normalized = is_normalized;
   }
   out.report = os.str();
-  out.nodes_evaluated = ev.nodes_evaluated;
+  out.nodes_evaluated += ev.nodes_evaluated;
   out.cache_hits = ev.cache_hits;
   return out;
 }

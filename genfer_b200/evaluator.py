@@ -37,7 +37,7 @@ class SgclResult:
 def parse_flags(source: str):
     """The `# flags: ...` first-line convention of the reference's test harness (tests/integration.rs:18-33)."""
     first = source.split("\n", 1)[0]
-    opts = {"limit": None, "no_probs": False, "no_simplify_gf": False, "unroll": 8, "bounds": False, "unsupported": []}
+    opts = {"limit": None, "no_probs": False, "no_simplify_gf": False, "unroll": 8, "bounds": False, "symbolic": False, "unsupported": []}
     if "flags:" not in first:
         return opts
     toks = first.split("flags:", 1)[1].split()
@@ -54,21 +54,24 @@ def parse_flags(source: str):
             opts["unroll"] = int(toks[i + 1]); i += 1
         elif t == "--bounds":
             opts["bounds"] = True
-        else:   # --rational, -s, --precision, --big-float: number modes that stay on the reference's CPU code
+        elif t in ("-s", "--symbolic"):
+            opts["symbolic"] = True
+        else:   # --rational, --precision, --big-float: number modes that stay on the reference's CPU code
             opts["unsupported"].append(t)
         i += 1
     return opts
 
 
 def run_sgcl(source: str, limit: Optional[int] = None, no_probs: bool = False, no_simplify_gf: bool = False,
-             unroll: int = 8, ctx: Optional[Context] = None, bounds: bool = False) -> SgclResult:
+             unroll: int = 8, ctx: Optional[Context] = None, bounds: bool = False, symbolic: bool = False) -> SgclResult:
     """`bounds`: the reference's `--bounds` mode -- the evaluator runs over TaylorPoly<Interval<F64>> on the device (gti_*) and
-    the report prints the enclosures."""
+    the report prints the enclosures.  `symbolic`: the reference's `-s` mode -- the generating function becomes one univariate
+    computation DAG (host) that is evaluated over TaylorExpansion<F64> on the device (gtu_*)."""
     ctx = ctx or default_context()
     lib = ctx.lib
     h = C.c_void_p()
     err = C.create_string_buffer(2048)
-    flags = (1 if no_probs else 0) | (2 if no_simplify_gf else 0) | (4 if bounds else 0)
+    flags = (1 if no_probs else 0) | (2 if no_simplify_gf else 0) | (4 if bounds else 0) | (8 if symbolic else 0)
     rc = lib.gtp_run_sgcl(ctx.h, source.encode(), -1 if limit is None else int(limit), flags, unroll, C.byref(h), err, 2048)
     if rc != 0:
         raise TaylorPanic(rc, err.value.decode())

@@ -234,7 +234,10 @@ int gtu_eq(gtp_ctx* ctx, const gtu_series* a, const gtu_series* b, int* out);   
  *   flags  : 1 = --no-probs, 2 = --no-simplify-gf, 4 = --bounds: run_program_intervals::<F64> (src/main.rs:145-185) -- the
  *            evaluator runs over TaylorPoly<Interval<F64>> on the device (gti_*), ratio constants are the enclosures
  *            Number::from_ratio builds (number/number.rs:26-33), the report prints "in [lo, hi]" lines (main.rs:291-299);
- *            the GenFun is evaluated unsimplified in this mode
+ *            the GenFun is evaluated unsimplified in this mode;
+ *            8 = -s / --symbolic (src/main.rs:196-209, src/symbolic.rs): the generating function becomes ONE univariate
+ *            computation DAG on the host (symbolic Taylor coefficients, evaluator/symbolic.hpp) and that DAG is evaluated
+ *            over TaylorExpansion<F64> through gtu_* (probs_symbolic / moments_symbolic :238-299); F64 only
  *   unroll : --unroll (reference default 8; only used by `while`)
  * On error (parse error, or anything the reference would panic on) returns GTP_ERR_INDEX and copies the message
  * into `err`.  The report is byte-compatible with the reference's stdout under --no-timing. */

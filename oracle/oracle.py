@@ -480,7 +480,7 @@ class SgclResult:
 
 
 def run_sgcl(source: str, limit: Optional[int] = None, no_probs: bool = False, no_simplify_gf: bool = False,
-             unroll: int = 8, bounds: bool = False) -> SgclResult:
+             unroll: int = 8, bounds: bool = False, symbolic: bool = False) -> SgclResult:
     """The host evaluator instantiated over the CPU oracle (oracle_eval.cpp): reference-order f64 arithmetic, or with
     `bounds` the reference's `--bounds` mode (TaylorPoly<Interval<F64>>, ratio constants enclosed by Number::from_ratio; the
     report prints intervals).  The interval mode is unpinned: no reference fixture runs with --bounds."""
@@ -495,7 +495,7 @@ def run_sgcl(source: str, limit: Optional[int] = None, no_probs: bool = False, n
     L.orc_sgcl_free.argtypes = [C.c_void_p]
     h = C.c_void_p()
     err = C.create_string_buffer(2048)
-    flags = (1 if no_probs else 0) | (2 if no_simplify_gf else 0) | (4 if bounds else 0)
+    flags = (1 if no_probs else 0) | (2 if no_simplify_gf else 0) | (4 if bounds else 0) | (8 if symbolic else 0)
     L.orc_sgcl_moment_bounds.argtypes = [C.c_void_p, _f64p]
     L.orc_sgcl_prob_bounds.argtypes = [C.c_void_p, _f64p]
     rc = L.orc_run_sgcl(source.encode(), -1 if limit is None else int(limit), flags, unroll, C.byref(h), err, 2048)

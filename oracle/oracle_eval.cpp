@@ -117,6 +117,23 @@ struct OracleBackendT {
     for (const T& x : a->coeffs.data) out.push_back(A::wrap(x));
     return out;
   }
+  // ---- TaylorExpansion<T> (univariate_taylor.rs) for the symbolic mode (only instantiated for T = f64) ----
+  using TE = orc::TaylorExpansion<T>;
+  using Uni = std::shared_ptr<const TE>;
+  static Uni umk(TE t) { return std::make_shared<const TE>(std::move(t)); }
+  Uni uni_constant(double x) { return umk(TE::constant(A::raw(Scalar(x)))); }
+  Uni uni_var(double x, size_t order) { return umk(TE::var(A::raw(Scalar(x)), order)); }
+  Uni uni_add(const Uni& a, const Uni& b) { return umk(orc::te_add(*a, *b)); }
+  Uni uni_mul(const Uni& a, const Uni& b) { return umk(orc::te_mul(*a, *b)); }
+  Uni uni_div(const Uni& a, const Uni& b) { return umk(orc::te_div(*a, *b)); }
+  Uni uni_exp(const Uni& a) { return umk(a->exp()); }
+  Uni uni_log(const Uni& a) { return umk(a->log()); }
+  Uni uni_pow(const Uni& a, uint32_t e) { return umk(orc::te_pow(*a, e)); }
+  Uni uni_max(const Uni& a, const Uni& b) {
+    if (!a->is_const || !b->is_const) throw gfe::EvalError("Maximum can only be applied to constant Taylor expansions.");
+    return umk(TE::constant(A::raw(A::max(A::wrap(a->c), A::wrap(b->c)))));
+  }
+  Scalar uni_coeff(const Uni& a, size_t order) { return A::wrap(a->coeff(order)); }
 };
 using OracleBackend = OracleBackendT<F64Scalar>;
 using IntervalBackend = OracleBackendT<IvScalar>;
@@ -135,6 +152,7 @@ int orc_run_sgcl(const char* source, int64_t limit, int flags, uint64_t unroll, 
     opt.no_probs = (flags & 1) != 0;
     opt.no_simplify_gf = (flags & 2) != 0;
     opt.bounds = (flags & 4) != 0;
+    opt.symbolic = (flags & 8) != 0;
     opt.unroll = (size_t)unroll;
     auto res = std::make_unique<orc_sgcl_result>();
     if (opt.bounds) {   // run_program_intervals::<F64> (main.rs:145-185)

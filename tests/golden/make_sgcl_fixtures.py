@@ -11,6 +11,7 @@ evaluator -- i.e. no --rational / --precision / -s / --bounds / --big-float (tho
 and no `skip integration test`.  `.expect` is the reference's stdout with --no-timing.
 Also copied: example.sgcl (BASELINE config C1) and the benchmarks/prodigy programs of config C5 (they have no .expect;
 their "Original code" comments quote exact rationals, checked in tests/test_sgcl_*.py).
+The `-s` (symbolic mode) fixtures go to tests/golden/sgcl_symbolic/.
 """
 import glob
 import os
@@ -59,6 +60,28 @@ def main():
     for prog in ("burglar_alarm", "max", "monty_hall", "monty_hall_nested", "grass", "fuzzy_or"):
         shutil.copy(os.path.join(REF, "benchmarks", "prodigy", prog + ".sgcl"), os.path.join(OUT, "config", prog + ".sgcl"))
     print(f"{n} fixture pairs + 7 config programs -> {OUT}")
+    symbolic()
+
+
+def symbolic():
+    """The reference's `-s` (symbolic mode) fixtures, kept apart from the f64 Taylor-mode ones: tests/golden/sgcl_symbolic/."""
+    out = os.path.join(HERE, "sgcl_symbolic")
+    if os.path.exists(out):
+        shutil.rmtree(out)
+    os.makedirs(out)
+    n = 0
+    for src in sorted(glob.glob(os.path.join(REF, "test", "expect", "**", "*.sgcl"), recursive=True)):
+        first = open(src).readline()
+        exp = src[:-5] + ".expect"
+        if "skip integration test" in first or "flags:" not in first or not os.path.exists(exp):
+            continue
+        flags = set(first.split("flags:", 1)[1].split())
+        if not ({"-s", "--symbolic"} & flags) or (flags & (OTHER_MODES - {"-s", "--symbolic"})):
+            continue
+        shutil.copy(src, os.path.join(out, os.path.basename(src)))
+        shutil.copy(exp, os.path.join(out, os.path.basename(exp)))
+        n += 1
+    print(f"{n} symbolic-mode fixture pairs -> {out}")
 
 
 if __name__ == "__main__":
