@@ -430,7 +430,18 @@ struct HornerDirectP {
   int add_mode;   // 0: product only, 1: Add general path, 2: Add scalar path
 };
 
-template <int NT, int U>
+// MODE: 0 product only (plain stencil product), 1 Add general path, 2 Add scalar path (compile-time: no mode branches and no
+// slice loads in the element loop of the other modes).
+// Source rows are read with ordinary (L1-allocating) loads: the shifted re-read of a row by the next term of its group is an L1
+// hit instead of a second trip to L2.  Data written by other CTAs in the previous step is ordered by the grid barrier (thread 0's
+// acquire fence after the spin + bar.sync, the same protocol as cooperative-groups grid.sync(), after which plain loads are
+// specified to observe it).
+__device__ __forceinline__ double ld_row(const double* p) {
+  double v;
+  asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+template <int NT, int U, int MODE>
 __global__ void __launch_bounds__(HD_T, (NT <= 4 ? 3 : (NT <= 8 ? 2 : 1))) k_horner_direct(const __grid_constant__ HornerDirectP dp) {
   const HornerP& p = dp.h;
   const int ne = p.ne;
@@ -440,8 +451,14 @@ __global__ void __launch_bounds__(HD_T, (NT <= 4 ? 3 : (NT <= 8 ? 2 : 1))) k_hor
   const unsigned lane = threadIdx.x & 31u;
   const unsigned warps_total = gridDim.x * (HD_T / 32), gw = blockIdx.x * (HD_T / 32) + (threadIdx.x >> 5);
   double sv[NT];
+  unsigned gstart = 0;   // bit t: term t starts a group
+  bool finite_sv = true;
 #pragma unroll
-  for (int t = 0; t < NT; t++) sv[t] = t < p.nt ? p.subst[p.sidx[t]] : 0.0;
+  for (int t = 0; t < NT; t++) {
+    sv[t] = t < p.nt ? p.subst[p.sidx[t]] : 0.0;
+    if (t < p.nt && p.group_start[t]) gstart |= 1u << t;
+    finite_sv = finite_sv && fabs(sv[t]) <= 1.7976931348623157e308;
+  }
   if (threadIdx.x == 0)
     for (int a = 0; a < HN_MAXE; a++) s_nxt[a] = a < ne ? p.shape0[a] : 1u;
   unsigned phase = 0;
@@ -457,7 +474,7 @@ __global__ void __launch_bounds__(HD_T, (NT <= 4 ? 3 : (NT <= 8 ? 2 : 1))) k_hor
       if (a < ne) {
         const unsigned long long s = (unsigned long long)ca + p.sshape[a] - 1ull;
         pa = (unsigned)min(s, (unsigned long long)p.d[a]);
-        na = dp.add_mode ? max(pa, p.slice[a]) : pa;
+        na = MODE ? max(pa, p.slice[a]) : pa;
       }
       long long st = 1;
 #pragma unroll
@@ -483,13 +500,13 @@ __global__ void __launch_bounds__(HD_T, (NT <= 4 ? 3 : (NT <= 8 ? 2 : 1))) k_hor
     for (unsigned item = gw; item < n_items; item += warps_total) {
       const unsigned row = item * G + sub;
       if (row >= rows) continue;
-      // ---- once per row: index, validity of the groups, source offsets of the terms ----
+      // ---- once per row: index, validity of the groups, per-term source pointer and valid column range ----
       bool in_prod = true, in_slice = true;
       long long so = 0;
       long long toff[NT];
       unsigned openmask = (p.nt >= 32) ? 0xffffffffu : ((1u << p.nt) - 1u);
 #pragma unroll
-      for (int t = 0; t < NT; t++) toff[t] = -(long long)p.m[t][ne - 1];
+      for (int t = 0; t < NT; t++) toff[t] = 0;
       {
         unsigned rem = row;
         for (int a = ne - 2; a >= 0; --a) {
@@ -508,62 +525,85 @@ __global__ void __launch_bounds__(HD_T, (NT <= 4 ? 3 : (NT <= 8 ? 2 : 1))) k_hor
           }
         }
       }
-      double* drow = dst + (size_t)row * L_out;
-      // ---- the row: U chunks per trip, every load of all chunks issued before the first use ----
-      // product of one coefficient in the reference's order; val(t) yields res[k - m_t] (only asked for in-range terms)
-      auto product = [&](unsigned cu, auto&& val) -> double {
-        double total_v = 0.0, inner = 0.0;
-        bool open = false;
+      // term t contributes to column c iff its group is open and c - m_t lies in the source row: (c - lo[t]) < span[t]
+      const double* tp[NT];
+      unsigned lo[NT], span[NT];
 #pragma unroll
-        for (int t = 0; t < NT; t++) {
-          if (t < p.nt) {
-            if (p.group_start[t]) {
+      for (int t = 0; t < NT; t++) {
+        const unsigned ml = (unsigned)p.m[t][ne - 1];
+        const bool ok = in_prod && ((openmask >> t) & 1u);
+        const unsigned hi = min(L_prod, L_src + ml);
+        lo[t] = ml;
+        span[t] = (ok && hi > ml) ? hi - ml : 0u;
+        tp[t] = src + (toff[t] - (long long)ml + (long long)c0);
+      }
+      double* drow = dst + ((size_t)row * L_out + c0);
+      const double* srow = slice_base + (so + (long long)c0 * slice_cstr);
+      const unsigned prod_end = in_prod ? L_prod : 0u, slice_end = (MODE == 1 && in_slice) ? L_slice : 0u;
+      // ---- the row: U chunks per trip, every load of all chunks issued before the first use ----
+      for (unsigned base = 0; base < L_out; base += U * W) {
+        double xv[U][NT], sl[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const unsigned idx = base + u * W, cu = idx + c0;
+#pragma unroll
+          for (int t = 0; t < NT; t++) xv[u][t] = (cu - lo[t]) < span[t] ? ld_row(tp[t] + idx) : 0.0;
+          if (MODE == 1) sl[u] = cu < slice_end ? srow[(long long)idx * slice_cstr] : 0.0;
+        }
+        if (finite_sv) {
+          // Branch-free arithmetic.  An absent term was loaded as +0.0 and contributes (+-0) to a sum that is never -0 (every
+          // sum starts from +0.0), a closed group contributes +0.0 to the total, a coefficient outside the product / the slice
+          // adds +0.0 to a value that is never -0: bit-identical to skipping them, as long as the substitution's coefficients
+          // are finite (0 * inf would not be) -- checked once per launch; otherwise the predicated form below runs.
+#pragma unroll
+          for (int u = 0; u < U; u++) {
+            const unsigned idx = base + u * W, cu = idx + c0;
+            double total_v = 0.0, inner = 0.0;
+#pragma unroll
+            for (int t = 0; t < NT; t++) {
+              if (t > 0 && ((gstart >> t) & 1u)) {
+                total_v = __dadd_rn(total_v, inner);
+                inner = 0.0;
+              }
+              inner = __dadd_rn(inner, __dmul_rn(xv[u][t], sv[t]));
+            }
+            total_v = __dadd_rn(total_v, inner);
+            double rv;
+            if (MODE == 0) rv = total_v;
+            else if (MODE == 2) rv = (row == 0 && cu == 0) ? __dadd_rn(total_v, slice_base[0]) : total_v;
+            else rv = __dadd_rn(__dadd_rn(0.0, total_v), sl[u]);
+            if (cu < L_out) drow[idx] = rv;
+          }
+          continue;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const unsigned idx = base + u * W, cu = idx + c0;
+          if (cu >= L_out) continue;
+          // the product in the reference's order: groups ascending, the innermost axis summed from zero and then added
+          double total_v = 0.0, inner = 0.0;
+          bool open = false;
+#pragma unroll
+          for (int t = 0; t < NT; t++) {
+            if ((gstart >> t) & 1u) {
               if (open) total_v = __dadd_rn(total_v, inner);
               inner = 0.0;
               open = (openmask >> t) & 1u;
             }
-            const unsigned cc = cu - (unsigned)p.m[t][ne - 1];
-            if (open && cc < L_src) inner = __dadd_rn(inner, __dmul_rn(val(t), sv[t]));
+            if ((cu - lo[t]) < span[t]) inner = __dadd_rn(inner, __dmul_rn(xv[u][t], sv[t]));
           }
-        }
-        if (open) total_v = __dadd_rn(total_v, inner);
-        return total_v;
-      };
-      auto finish = [&](unsigned cu, bool a_ok, double prod, double slv) {
-        double rv;
-        if (dp.add_mode == 0) rv = prod;
-        else if (dp.add_mode == 2) rv = (row == 0 && cu == 0) ? __dadd_rn(prod, slice_base[0]) : prod;
-        else {
-          rv = 0.0;
-          if (a_ok) rv = __dadd_rn(rv, prod);
-          if (in_slice && cu < L_slice) rv = __dadd_rn(rv, slv);
-        }
-        drow[cu] = rv;
-      };
-      {
-        for (unsigned base = 0; base < L_out; base += U * W) {
-          const unsigned c = base + c0;
-          double xv[U][NT], sl[U];
-#pragma unroll
-          for (int u = 0; u < U; u++) {
-            const unsigned cu = c + u * W;
-            const bool a_ok = in_prod && cu < L_prod;
-#pragma unroll
-            for (int t = 0; t < NT; t++) {
-              const unsigned cc = cu - (unsigned)p.m[t][ne - 1];
-              const bool ld = a_ok && ((openmask >> t) & 1u) && cc < L_src;   // out-of-range terms of an absent group are never used
-              xv[u][t] = ld ? ldcg(src + (toff[t] + (long long)cu)) : 0.0;
-            }
-            sl[u] = (dp.add_mode == 1 && in_slice && cu < L_slice) ? slice_base[so + (long long)cu * slice_cstr] : 0.0;
+          if (open) total_v = __dadd_rn(total_v, inner);
+          const bool a_ok = cu < prod_end;
+          const double prod = a_ok ? total_v : 0.0;
+          double rv;
+          if (MODE == 0) rv = prod;
+          else if (MODE == 2) rv = (row == 0 && cu == 0) ? __dadd_rn(prod, slice_base[0]) : prod;
+          else {
+            rv = 0.0;
+            if (a_ok) rv = __dadd_rn(rv, prod);
+            if (cu < slice_end) rv = __dadd_rn(rv, sl[u]);
           }
-#pragma unroll
-          for (int u = 0; u < U; u++) {
-            const unsigned cu = c + u * W;
-            if (cu >= L_out) continue;
-            const bool a_ok = in_prod && cu < L_prod;
-            const double prod = a_ok ? product(cu, [&](int t) { return xv[u][t]; }) : 0.0;
-            finish(cu, a_ok, prod, sl[u]);
-          }
+          drow[idx] = rv;
         }
       }
     }
@@ -590,12 +630,15 @@ static bool launch_direct_variant(Ctx& ctx, const HornerP& p, int add_mode, cons
   if (c < 0) return false;
   const void* fn;
   int bucket;
-  if (p.nt <= 2) { fn = (const void*)k_horner_direct<2, 4>; bucket = 0; }
-  else if (p.nt <= 4) { fn = (const void*)k_horner_direct<4, 2>; bucket = 1; }
-  else if (p.nt <= 8) { fn = (const void*)k_horner_direct<8, 2>; bucket = 2; }
-  else if (p.nt <= 16) { fn = (const void*)k_horner_direct<16, 1>; bucket = 3; }
-  else { fn = (const void*)k_horner_direct<32, 1>; bucket = 4; }
-  static int per_sm_cached[10][64] = {};
+#define HD_PICK(NT_, U_) (add_mode == 0 ? (const void*)k_horner_direct<NT_, U_, 0> : (add_mode == 1 ? (const void*)k_horner_direct<NT_, U_, 1> : (const void*)k_horner_direct<NT_, U_, 2>))
+  if (p.nt <= 2) { fn = HD_PICK(2, 4); bucket = 0; }
+  else if (p.nt <= 4) { fn = HD_PICK(4, 2); bucket = 1; }
+  else if (p.nt <= 8) { fn = HD_PICK(8, 2); bucket = 2; }
+  else if (p.nt <= 16) { fn = HD_PICK(16, 1); bucket = 3; }
+  else { fn = HD_PICK(32, 1); bucket = 4; }
+#undef HD_PICK
+  bucket = bucket * 3 + add_mode;
+  static int per_sm_cached[15][64] = {};
   int& per_sm = per_sm_cached[bucket][ctx.device & 63];
   if (per_sm == 0) {
     GTP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, HD_T, 0));
