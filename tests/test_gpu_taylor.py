@@ -426,6 +426,24 @@ def test_row_walking_horner_kernel_on_every_case():
             g, gs = genfer_b200.TaylorPoly.new(a, deg, ctx), genfer_b200.TaylorPoly.new(sub, deg, ctx)
             o, os_ = O.TaylorPoly.new(a, deg), O.TaylorPoly.new(sub, deg)
             assert_same(g.subst_var(v, gs), o.subst_var(v, os_))
+        # signed zeros and exact cancellations go through the branch-free arithmetic (absent terms add +-0): still the same bits
+        rng = np.random.default_rng(99)
+        a = rng.integers(-2, 3, size=(40, 6, 70)).astype(np.float64)
+        a[a == 0] = np.where(rng.random(np.count_nonzero(a == 0)) < 0.5, -0.0, 0.0)
+        sub = np.array([[[-0.0, 1.0]], [[-1.0, 0.0]]])
+        deg = (50, 6, 90)
+        g, gs = genfer_b200.TaylorPoly.new(a, deg, ctx), genfer_b200.TaylorPoly.new(sub, deg, ctx)
+        o, os_ = O.TaylorPoly.new(a, deg), O.TaylorPoly.new(sub, deg)
+        for v in (0, 2):
+            assert_same(g.subst_var(v, gs), o.subst_var(v, os_))
+        # a non-finite substitution coefficient takes the predicated form (0 * inf must not reach coefficients the reference
+        # never multiplies): same NaN positions, same bits everywhere else
+        sub2 = np.array([[[0.5, np.inf]], [[-1.0, 2.0]]])
+        gs2, os2 = genfer_b200.TaylorPoly.new(sub2, deg, ctx), O.TaylorPoly.new(sub2, deg)
+        ga, oa = g.subst_var(2, gs2).array(), o.subst_var(2, os2).array()
+        assert ga.shape == oa.shape and np.array_equal(np.isnan(ga), np.isnan(oa))
+        ok = ~np.isnan(oa)
+        assert np.array_equal(ga[ok].view(np.uint64), oa[ok].view(np.uint64))
     finally:
         ctx.close()
 
