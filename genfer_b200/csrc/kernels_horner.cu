@@ -442,7 +442,7 @@ __device__ __forceinline__ double ld_row(const double* p) {
   return v;
 }
 template <int NT, int U, int MODE>
-__global__ void __launch_bounds__(HD_T, (NT <= 4 ? 3 : (NT <= 8 ? 2 : 1))) k_horner_direct(const __grid_constant__ HornerDirectP dp) {
+__global__ void __launch_bounds__(HD_T, (NT <= 4 ? (MODE == 0 ? 4 : 3) : (NT <= 8 ? 2 : 1))) k_horner_direct(const __grid_constant__ HornerDirectP dp) {
   const HornerP& p = dp.h;
   const int ne = p.ne;
   // step-constant extents and strides live in shared memory (they would cost ~50 registers as unrolled arrays)
@@ -494,116 +494,155 @@ __global__ void __launch_bounds__(HD_T, (NT <= 4 ? 3 : (NT <= 8 ? 2 : 1))) k_hor
     unsigned W = 32;                       // lanes per row
     while (W > 1 && (W >> 1) >= L_out) W >>= 1;
     const unsigned G = 32u / W, sub = lane / W, c0 = lane & (W - 1u);
-    const unsigned n_items = (rows + G - 1) / G;
     const double* slice_base = p.self + (long long)i * p.self_vstr;
     const long long slice_cstr = p.selfstr[ne - 1];
+    // Long rows (one row per warp at a time): every warp owns ONE contiguous range of rows -- balanced to within a row -- and
+    // walks it: the first row is decoded in full, the following ones advance the index of the last row axis by one (pointers
+    // move by one stride, no division) until that index wraps.  Short rows (several per warp): one group of rows per item.
+    const unsigned n_items = G == 1u ? warps_total : (rows + G - 1) / G;
+    const int al = ne - 2;   // the last row axis (>= 0: the kernel needs two effective axes)
+    const unsigned n_last = s_nxt[al], c_last = s_cur[al], p_last = s_prodsh[al], sl_last = p.slice[al];
+    const long long sa_last = s_cstr[al], self_last = p.selfstr[al];
     for (unsigned item = gw; item < n_items; item += warps_total) {
-      const unsigned row = item * G + sub;
-      if (row >= rows) continue;
-      // ---- once per row: index, validity of the groups, per-term source pointer and valid column range ----
-      bool in_prod = true, in_slice = true;
+      unsigned row, row_end;
+      if (G == 1u) {
+        row = (unsigned)(((unsigned long long)item * rows) / warps_total);
+        row_end = (unsigned)(((unsigned long long)(item + 1u) * rows) / warps_total);
+      } else {
+        row = item * G + sub;
+        row_end = row < rows ? row + 1u : row;
+      }
+      bool need_full = true;
+      bool in_prod_o = true, in_slice_o = true;
+      unsigned open_o = 0, k_last = 0;
       long long so = 0;
-      long long toff[NT];
-      unsigned openmask = (p.nt >= 32) ? 0xffffffffu : ((1u << p.nt) - 1u);
-#pragma unroll
-      for (int t = 0; t < NT; t++) toff[t] = 0;
-      {
-        unsigned rem = row;
-        for (int a = ne - 2; a >= 0; --a) {
-          const unsigned na = s_nxt[a], ca = s_cur[a];
-          const long long sa = s_cstr[a];
-          const unsigned q = rem / na, ka = rem - q * na;
-          rem = q;
-          in_prod = in_prod && ka < s_prodsh[a];
-          in_slice = in_slice && ka < p.slice[a];
-          so += (long long)ka * p.selfstr[a];
-#pragma unroll
-          for (int t = 0; t < NT; t++) {
-            const unsigned idx = ka - (unsigned)p.m[t][a];
-            if (idx >= ca) openmask &= ~(1u << t);
-            toff[t] += (long long)idx * sa;
-          }
-        }
-      }
-      // term t contributes to column c iff its group is open and c - m_t lies in the source row: (c - lo[t]) < span[t]
       const double* tp[NT];
-      unsigned lo[NT], span[NT];
+      for (; row < row_end; row++) {
+        if (need_full) {
+          // ---- full decode: outer axes folded into flags / offsets, the last row axis kept as k_last ----
+          in_prod_o = in_slice_o = true;
+          so = 0;
+          long long toff[NT];
+          open_o = (p.nt >= 32) ? 0xffffffffu : ((1u << p.nt) - 1u);
 #pragma unroll
-      for (int t = 0; t < NT; t++) {
-        const unsigned ml = (unsigned)p.m[t][ne - 1];
-        const bool ok = in_prod && ((openmask >> t) & 1u);
-        const unsigned hi = min(L_prod, L_src + ml);
-        lo[t] = ml;
-        span[t] = (ok && hi > ml) ? hi - ml : 0u;
-        tp[t] = src + (toff[t] - (long long)ml + (long long)c0);
-      }
-      double* drow = dst + ((size_t)row * L_out + c0);
-      const double* srow = slice_base + (so + (long long)c0 * slice_cstr);
-      const unsigned prod_end = in_prod ? L_prod : 0u, slice_end = (MODE == 1 && in_slice) ? L_slice : 0u;
-      // ---- the row: U chunks per trip, every load of all chunks issued before the first use ----
-      for (unsigned base = 0; base < L_out; base += U * W) {
-        double xv[U][NT], sl[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-          const unsigned idx = base + u * W, cu = idx + c0;
-#pragma unroll
-          for (int t = 0; t < NT; t++) xv[u][t] = (cu - lo[t]) < span[t] ? ld_row(tp[t] + idx) : 0.0;
-          if (MODE == 1) sl[u] = cu < slice_end ? srow[(long long)idx * slice_cstr] : 0.0;
-        }
-        if (finite_sv) {
-          // Branch-free arithmetic.  An absent term was loaded as +0.0 and contributes (+-0) to a sum that is never -0 (every
-          // sum starts from +0.0), a closed group contributes +0.0 to the total, a coefficient outside the product / the slice
-          // adds +0.0 to a value that is never -0: bit-identical to skipping them, as long as the substitution's coefficients
-          // are finite (0 * inf would not be) -- checked once per launch; otherwise the predicated form below runs.
-#pragma unroll
-          for (int u = 0; u < U; u++) {
-            const unsigned idx = base + u * W, cu = idx + c0;
-            double total_v = 0.0, inner = 0.0;
+          for (int t = 0; t < NT; t++) toff[t] = 0;
+          unsigned rem = row;
+          {
+            const unsigned q = rem / n_last;
+            k_last = rem - q * n_last;
+            rem = q;
+          }
+          for (int a = al - 1; a >= 0; --a) {
+            const unsigned na = s_nxt[a], ca = s_cur[a];
+            const long long sa = s_cstr[a];
+            const unsigned q = rem / na, ka = rem - q * na;
+            rem = q;
+            in_prod_o = in_prod_o && ka < s_prodsh[a];
+            in_slice_o = in_slice_o && ka < p.slice[a];
+            so += (long long)ka * p.selfstr[a];
 #pragma unroll
             for (int t = 0; t < NT; t++) {
-              if (t > 0 && ((gstart >> t) & 1u)) {
-                total_v = __dadd_rn(total_v, inner);
-                inner = 0.0;
-              }
-              inner = __dadd_rn(inner, __dmul_rn(xv[u][t], sv[t]));
+              const unsigned idx = ka - (unsigned)p.m[t][a];
+              if (idx >= ca) open_o &= ~(1u << t);
+              toff[t] += (long long)idx * sa;
             }
-            total_v = __dadd_rn(total_v, inner);
-            double rv;
-            if (MODE == 0) rv = total_v;
-            else if (MODE == 2) rv = (row == 0 && cu == 0) ? __dadd_rn(total_v, slice_base[0]) : total_v;
-            else rv = __dadd_rn(__dadd_rn(0.0, total_v), sl[u]);
-            if (cu < L_out) drow[idx] = rv;
           }
-          continue;
+          so += (long long)k_last * self_last;
+#pragma unroll
+          for (int t = 0; t < NT; t++)
+            tp[t] = src + (toff[t] + ((long long)k_last - (long long)p.m[t][al]) * sa_last - (long long)p.m[t][ne - 1] + (long long)c0);
+          need_full = false;
         }
+        // ---- per row: the last row axis ----
+        const bool in_prod = in_prod_o && k_last < p_last, in_slice = in_slice_o && k_last < sl_last;
+        unsigned openmask = open_o;
+        unsigned lo[NT], span[NT];
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-          const unsigned idx = base + u * W, cu = idx + c0;
-          if (cu >= L_out) continue;
-          // the product in the reference's order: groups ascending, the innermost axis summed from zero and then added
-          double total_v = 0.0, inner = 0.0;
-          bool open = false;
-#pragma unroll
-          for (int t = 0; t < NT; t++) {
-            if ((gstart >> t) & 1u) {
-              if (open) total_v = __dadd_rn(total_v, inner);
-              inner = 0.0;
-              open = (openmask >> t) & 1u;
+        for (int t = 0; t < NT; t++) {
+          if ((k_last - (unsigned)p.m[t][al]) >= c_last) openmask &= ~(1u << t);
+          const unsigned ml = (unsigned)p.m[t][ne - 1];
+          const bool ok = in_prod && ((openmask >> t) & 1u);
+          const unsigned hi = min(L_prod, L_src + ml);
+          lo[t] = ml;
+          span[t] = (ok && hi > ml) ? hi - ml : 0u;
+        }
+        double* drow = dst + ((size_t)row * L_out + c0);
+        const double* srow = slice_base + (so + (long long)c0 * slice_cstr);
+        const unsigned prod_end = in_prod ? L_prod : 0u, slice_end = (MODE == 1 && in_slice) ? L_slice : 0u;
+        // ---- the row: U chunks per trip, every load of all chunks issued before the first use ----
+        for (unsigned base = 0; base < L_out; base += U * W) {
+          double xv[U][NT], sl[U];
+  #pragma unroll
+          for (int u = 0; u < U; u++) {
+            const unsigned idx = base + u * W, cu = idx + c0;
+  #pragma unroll
+            for (int t = 0; t < NT; t++) xv[u][t] = (cu - lo[t]) < span[t] ? ld_row(tp[t] + idx) : 0.0;
+            if (MODE == 1) sl[u] = cu < slice_end ? srow[(long long)idx * slice_cstr] : 0.0;
+          }
+          if (finite_sv) {
+            // Branch-free arithmetic.  An absent term was loaded as +0.0 and contributes (+-0) to a sum that is never -0 (every
+            // sum starts from +0.0), a closed group contributes +0.0 to the total, a coefficient outside the product / the slice
+            // adds +0.0 to a value that is never -0: bit-identical to skipping them, as long as the substitution's coefficients
+            // are finite (0 * inf would not be) -- checked once per launch; otherwise the predicated form below runs.
+  #pragma unroll
+            for (int u = 0; u < U; u++) {
+              const unsigned idx = base + u * W, cu = idx + c0;
+              double total_v = 0.0, inner = 0.0;
+  #pragma unroll
+              for (int t = 0; t < NT; t++) {
+                if (t > 0 && ((gstart >> t) & 1u)) {
+                  total_v = __dadd_rn(total_v, inner);
+                  inner = 0.0;
+                }
+                inner = __dadd_rn(inner, __dmul_rn(xv[u][t], sv[t]));
+              }
+              total_v = __dadd_rn(total_v, inner);
+              double rv;
+              if (MODE == 0) rv = total_v;
+              else if (MODE == 2) rv = (row == 0 && cu == 0) ? __dadd_rn(total_v, slice_base[0]) : total_v;
+              else rv = __dadd_rn(__dadd_rn(0.0, total_v), sl[u]);
+              if (cu < L_out) drow[idx] = rv;
             }
-            if ((cu - lo[t]) < span[t]) inner = __dadd_rn(inner, __dmul_rn(xv[u][t], sv[t]));
+            continue;
           }
-          if (open) total_v = __dadd_rn(total_v, inner);
-          const bool a_ok = cu < prod_end;
-          const double prod = a_ok ? total_v : 0.0;
-          double rv;
-          if (MODE == 0) rv = prod;
-          else if (MODE == 2) rv = (row == 0 && cu == 0) ? __dadd_rn(prod, slice_base[0]) : prod;
-          else {
-            rv = 0.0;
-            if (a_ok) rv = __dadd_rn(rv, prod);
-            if (cu < slice_end) rv = __dadd_rn(rv, sl[u]);
+  #pragma unroll
+          for (int u = 0; u < U; u++) {
+            const unsigned idx = base + u * W, cu = idx + c0;
+            if (cu >= L_out) continue;
+            // the product in the reference's order: groups ascending, the innermost axis summed from zero and then added
+            double total_v = 0.0, inner = 0.0;
+            bool open = false;
+  #pragma unroll
+            for (int t = 0; t < NT; t++) {
+              if ((gstart >> t) & 1u) {
+                if (open) total_v = __dadd_rn(total_v, inner);
+                inner = 0.0;
+                open = (openmask >> t) & 1u;
+              }
+              if ((cu - lo[t]) < span[t]) inner = __dadd_rn(inner, __dmul_rn(xv[u][t], sv[t]));
+            }
+            if (open) total_v = __dadd_rn(total_v, inner);
+            const bool a_ok = cu < prod_end;
+            const double prod = a_ok ? total_v : 0.0;
+            double rv;
+            if (MODE == 0) rv = prod;
+            else if (MODE == 2) rv = (row == 0 && cu == 0) ? __dadd_rn(prod, slice_base[0]) : prod;
+            else {
+              rv = 0.0;
+              if (a_ok) rv = __dadd_rn(rv, prod);
+              if (cu < slice_end) rv = __dadd_rn(rv, sl[u]);
+            }
+            drow[idx] = rv;
           }
-          drow[idx] = rv;
+        }
+        // ---- advance to the next row of the block ----
+        k_last++;
+        if (k_last == n_last) {
+          need_full = true;
+        } else {
+          so += self_last;
+#pragma unroll
+          for (int t = 0; t < NT; t++) tp[t] += sa_last;
         }
       }
     }
@@ -616,6 +655,7 @@ static bool launch_direct_variant(Ctx& ctx, const HornerP& p, int add_mode, cons
   if (!ctx.use_direct || p.ne < 2) return false;
   const unsigned L_final = final_shape[p.ne - 1];
   if (L_final < 48 || final_total < ctx.direct_min) return false;   // short rows: the per-row setup dominates
+  if (add_mode == 0 && L_final < 192 && !ctx.direct_products_all) return false;   // plain products: the gather kernel wins on shorter rows
   HornerDirectP dp;
   memset(&dp, 0, sizeof(dp));
   dp.h = p;
@@ -875,6 +915,16 @@ bool launch_horner(Ctx& ctx, const double* self, const Shape& self_shape, u64 v,
 bool launch_stencil_rows(Ctx& ctx, const MulArgs& a) {
   const int nd = a.ndim;
   if (a.accumulate || !a.rows.empty() || nd < 2 || a.row_begin != 0 || a.row_step != 1 || a.row_count != a.rs[0]) return false;
+  {  // cheap rejections first: this sits on the path of every small-operand product, most of them tiny
+    u64 total = 1, last = 1;
+    for (int d = 0; d < nd; d++) {
+      total *= a.rs[d];
+      if (a.rs[d] > 1) last = a.rs[d];
+    }
+    const bool direct = ctx.direct_products && ctx.use_direct && total >= ctx.direct_min && (last >= 192 || ctx.direct_products_all);
+    const bool bulk = ctx.bulk_products && ctx.use_bulk && total >= (1u << 18);
+    if (!direct && !bulk) return false;
+  }
   const u64 nx = prod(a.xs), ny = prod(a.ys);
   const bool small_is_x = nx <= ny;
   const Shape& ss = small_is_x ? a.xs : a.ys;

@@ -1,5 +1,5 @@
 """Developer tool: a few launches of the small-operand product (ncu / A-B target).
-usage: one_stencil.py [fast_mul mode] [case]   cases: 0 = [297,282,297] x [2,1,2], 1 = 16^6 x [2,1,2,1,1,2], 2 = [52]^4 x [2,2,1,2]"""
+usage: one_stencil.py [fast_mul mode: 1 default, 131073 gather kernel, 262145 row-walking kernel for any row length] [case]   cases: 0 = [297,282,297] x [2,1,2], 1 = 16^6 x [2,1,2,1,1,2], 2 = [52]^4 x [2,2,1,2]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, genfer_b200
