@@ -199,8 +199,16 @@ __global__ void __launch_bounds__(256) k_ew2d(const __grid_constant__ Ew2dParams
   const unsigned long long nq = (p.total + 3ull) / 4ull;
   for (unsigned long long qd = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; qd < nq; qd += (unsigned long long)gridDim.x * blockDim.x) {
     const unsigned long long o0 = qd * 4ull;
-    unsigned long long r = o0 / p.cols;
-    unsigned c = (unsigned)(o0 - r * p.cols);
+    unsigned long long r;
+    unsigned c;
+    if (p.total <= 0xffffffffull) {   // 32-bit division: the 64-bit one costs more instructions than the rest of the thread's work
+      const unsigned o32 = (unsigned)o0, r32 = o32 / (unsigned)p.cols;
+      r = r32;
+      c = o32 - r32 * (unsigned)p.cols;
+    } else {
+      r = o0 / p.cols;
+      c = (unsigned)(o0 - r * p.cols);
+    }
     double v[4];
     unsigned fi[4];
     bool live[4];
