@@ -379,6 +379,8 @@ def run_ours(args):
         ids = [genfer_b200.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         ctx = genfer_b200.Context.create_group(local, rank, world, ids[0], stream=stream.cuda_stream)
+        if d ** n < 10 ** 7:   # gtp_mul partitions from 1e7 result coefficients by default (north_star); smaller sweep points on request
+            ctx.set_partition_threshold(d ** n)
     else:
         ctx = genfer_b200.Context(local, stream=stream.cuda_stream)
     kind = ctx.mul_kernel_kind(shape, shape, shape)
