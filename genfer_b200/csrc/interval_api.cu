@@ -176,11 +176,10 @@ struct IvLevP {
   int has_seed;
   Iv seed;           // exp / log of the constant term from the host's libm when the host knows it
 };
-__global__ void __launch_bounds__(128) k_iv_level(const IvLevP p, unsigned level) {
-  const u64 gstride = (u64)gridDim.x * blockDim.x;
+__device__ __forceinline__ void iv_level_body(const IvLevP& p, unsigned level, u64 first, u64 gstride) {
   const int ne = p.ne;
   const Iv zero = gti::iv(0.0, 0.0);
-  for (u64 lin = (u64)blockIdx.x * blockDim.x + threadIdx.x; lin < p.outer_total; lin += gstride) {
+  for (u64 lin = first; lin < p.outer_total; lin += gstride) {
     unsigned k[IVE];
     u64 rem = lin;
     unsigned sum = 0;
@@ -319,6 +318,18 @@ __global__ void __launch_bounds__(128) k_iv_level(const IvLevP p, unsigned level
       p.q[ro] = qv;
       p.r[ro] = gti::iv_div(qv, gti::iv_from_u32(k[a]));
     }
+  }
+}
+
+__global__ void __launch_bounds__(128) k_iv_level(const IvLevP p, unsigned level) {
+  iv_level_body(p, level, (u64)blockIdx.x * blockDim.x + threadIdx.x, (u64)gridDim.x * blockDim.x);
+}
+// Small tensors (1-d and thin 2-d series: hundreds of levels of a handful of coefficients each): ALL levels in one single-CTA
+// launch, a block barrier between levels (the level's coefficients are written and read by this CTA only).
+__global__ void __launch_bounds__(256) k_iv_levels_cta(const IvLevP p, unsigned levels) {
+  for (unsigned level = 0; level < levels; level++) {
+    iv_level_body(p, level, threadIdx.x, blockDim.x);
+    __syncthreads();
   }
 }
 
@@ -612,6 +623,10 @@ void run_levels(Ctx& c, int op, const gti_poly& x, const gti_poly* y, gti_poly& 
   }
   p.has_seed = seed ? 1 : 0;
   if (seed) p.seed = *seed;
+  if (p.outer_total <= 2048 && levels <= (1u << 20)) {
+    GTP_LAUNCH(c, k_iv_levels_cta, 1, 256, 0, p, (unsigned)levels);
+    return;
+  }
   const int grid = (int)std::max<u64>(1, std::min<u64>((p.outer_total + 127) / 128, (u64)c.sm_count * 32));
   for (u64 t = 0; t < levels; t++) GTP_LAUNCH(c, k_iv_level, grid, 128, 0, p, (unsigned)t);
 }
