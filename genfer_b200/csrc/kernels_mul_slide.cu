@@ -84,26 +84,42 @@ template <int LT> __device__ __forceinline__ void sl_flush(double (&z)[LT], doub
 }
 // z0 += x (*) ya ; z1 += x (*) yb   (both `lo` or both `hi`)
 template <int LT, bool HI>
+__device__ __forceinline__ void sl_col(double (&z0)[LT], double (&z1)[LT], const double (&ya)[LT], const double (&yb)[LT], const double xj,
+                                       const int jj) {
+  if (!HI) {
+#pragma unroll
+    for (int kk = jj; kk < LT; kk++) z0[kk] = fma(xj, ya[kk - jj], z0[kk]);
+#pragma unroll
+    for (int kk = jj; kk < LT; kk++) z1[kk] = fma(xj, yb[kk - jj], z1[kk]);
+  } else {
+#pragma unroll
+    for (int kk = 0; kk < jj; kk++) z0[kk] = fma(xj, ya[LT + kk - jj], z0[kk]);
+#pragma unroll
+    for (int kk = 0; kk < jj; kk++) z1[kk] = fma(xj, yb[LT + kk - jj], z1[kk]);
+  }
+}
+// A row convolution is a triangle: column j of x feeds LT - j (lo) or j (hi) accumulators, and every accumulator is a chain of
+// dependent DFMAs over j.  Walking the columns in ascending order ends (lo) or starts (hi) with a run of narrow columns whose
+// FMAs depend on each other at a distance below the DFMA latency.  The columns are therefore visited from both ends alternately
+// (0, LT-1, 1, LT-2, ..): a narrow column is always followed by a wide one.  The summation order differs from the reference's;
+// the DFMA kernels are tolerance-level anyway (contracted multiply-adds, RED.ADD meeting order).
+template <int LT, bool HI>
 __device__ __forceinline__ void sl_step(double (&z0)[LT], double (&z1)[LT], const double (&ya)[LT], const double (&yb)[LT],
                                         const double* __restrict__ xs) {
+  static_assert(LT % 4 == 0 || LT % 4 == 2, "even chunk");
 #pragma unroll
-  for (int j = 0; j < LT; j += 2) {
-    double2 xv = *reinterpret_cast<const double2*>(xs + j);
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const double xj = h ? xv.y : xv.x;
-      const int jj = j + h;
-      if (!HI) {
-#pragma unroll
-        for (int kk = jj; kk < LT; kk++) z0[kk] = fma(xj, ya[kk - jj], z0[kk]);
-#pragma unroll
-        for (int kk = jj; kk < LT; kk++) z1[kk] = fma(xj, yb[kk - jj], z1[kk]);
-      } else {
-#pragma unroll
-        for (int kk = 0; kk < jj; kk++) z0[kk] = fma(xj, ya[LT + kk - jj], z0[kk]);
-#pragma unroll
-        for (int kk = 0; kk < jj; kk++) z1[kk] = fma(xj, yb[LT + kk - jj], z1[kk]);
-      }
+  for (int j = 0; j < LT / 2; j += 2) {
+    const double2 xa = *reinterpret_cast<const double2*>(xs + j);             // columns j, j + 1
+    const int jb = LT - 2 - j;                                                // columns jb, jb + 1
+    if (jb > j) {
+      const double2 xb = *reinterpret_cast<const double2*>(xs + jb);
+      sl_col<LT, HI>(z0, z1, ya, yb, xa.x, j);
+      sl_col<LT, HI>(z0, z1, ya, yb, xb.y, jb + 1);
+      sl_col<LT, HI>(z0, z1, ya, yb, xa.y, j + 1);
+      sl_col<LT, HI>(z0, z1, ya, yb, xb.x, jb);
+    } else {   // the middle pair of a chunk whose half is odd (LT = 10, 14)
+      sl_col<LT, HI>(z0, z1, ya, yb, xa.x, j);
+      sl_col<LT, HI>(z0, z1, ya, yb, xa.y, j + 1);
     }
   }
 }
