@@ -113,3 +113,16 @@ def test_from_ratio_enclosures():
     assert lo < 0.5 < hi and hi - lo <= 4 * 2.0 ** -53
     f = O.run_sgcl(src)
     assert f.probs[1] == 0.5
+
+
+def test_from_ratio_with_a_denominator_beyond_32_bits():
+    """Number::from_ratio splits numerator and denominator into 32-bit halves (number/number.rs:26-33); for Interval<F64> the
+    recombination `hi * 2^32 + lo` is itself interval arithmetic, so the constant's enclosure is a few ulps wide -- it must still
+    contain both the exact ratio and the f64 quotient the f64 path uses."""
+    from fractions import Fraction
+    src = "X ~ Bernoulli(0.0000000001);\nreturn X;\n"          # 1 / 10^10, 10^10 > 2^32
+    b = O.run_sgcl(src, bounds=True)
+    lo, hi = b.prob_bounds[1]
+    assert Fraction(lo) <= Fraction(1, 10 ** 10) <= Fraction(hi)
+    assert lo <= 1e-10 <= hi and (hi - lo) <= 16 * 2.0 ** -53 * 1e-10
+    assert O.run_sgcl(src).probs[1] == 1.0 / 1e10
