@@ -503,6 +503,111 @@ __global__ void __launch_bounds__(HD_T, (NT <= 4 ? (MODE == 0 ? 4 : 3) : (NT <= 
     const int al = ne - 2;   // the last row axis (>= 0: the kernel needs two effective axes)
     const unsigned n_last = s_nxt[al], c_last = s_cur[al], p_last = s_prodsh[al], sl_last = p.slice[al];
     const long long sa_last = s_cstr[al], self_last = p.selfstr[al];
+    // ---- short rows (at most 32 coefficients) under at least two row axes: the last TWO axes are walked as one contiguous block
+    // of the output (n_last rows of L_out), every lane busy; the row index inside the block comes from a multiply-high ----
+    if (ne >= 3 && L_out <= 32u) {
+      const unsigned BS = n_last * L_out, n_or = rows / n_last;
+      const unsigned want = (warps_total + n_or - 1u) / n_or;                       // chunks per block that keep every warp busy
+      const unsigned nchunk = max(1u, min((BS + 63u) / 64u, want));
+      const unsigned CH = (((BS + nchunk - 1u) / nchunk) + 31u) & ~31u;
+      const unsigned magic = (unsigned)(0x100000000ull / L_out) + 1u;                // e / L_out = umulhi(e, magic) for e < 2^32 / L_out
+      unsigned mr[NT], ml[NT];
+#pragma unroll
+      for (int t = 0; t < NT; t++) { mr[t] = (unsigned)p.m[t][al]; ml[t] = (unsigned)p.m[t][ne - 1]; }
+      for (unsigned item = gw; item < n_or * nchunk; item += warps_total) {
+        const unsigned orow = item / nchunk, e_begin = (item - orow * nchunk) * CH, e_end = min(BS, e_begin + CH);
+        bool in_prod_o = true, in_slice_o = true;
+        unsigned open_o = (p.nt >= 32) ? 0xffffffffu : ((1u << p.nt) - 1u);
+        long long so = 0, toff[NT];
+#pragma unroll
+        for (int t = 0; t < NT; t++) toff[t] = 0;
+        {
+          unsigned rem = orow;
+          for (int a = al - 1; a >= 0; --a) {
+            const unsigned na = s_nxt[a], ca = s_cur[a];
+            const long long sa = s_cstr[a];
+            const unsigned q = rem / na, ka = rem - q * na;
+            rem = q;
+            in_prod_o = in_prod_o && ka < s_prodsh[a];
+            in_slice_o = in_slice_o && ka < p.slice[a];
+            so += (long long)ka * p.selfstr[a];
+#pragma unroll
+            for (int t = 0; t < NT; t++) {
+              const unsigned idx = ka - (unsigned)p.m[t][a];
+              if (idx >= ca) open_o &= ~(1u << t);
+              toff[t] += (long long)idx * sa;
+            }
+          }
+        }
+        if (!in_prod_o) open_o = 0;
+        const unsigned pk = in_prod_o ? p_last : 0u, sk = (MODE == 1 && in_slice_o) ? sl_last : 0u;
+        double* dblk = dst + (size_t)orow * BS;
+        const double* sblk = slice_base + so;
+        for (unsigned base = e_begin; base < e_end; base += U * 32u) {
+          double xv[U][NT], sl[U];
+          unsigned vm[U];
+#pragma unroll
+          for (int u = 0; u < U; u++) {
+            const unsigned e = base + u * 32u + lane;
+            const unsigned kk = __umulhi(e, magic), c = e - kk * L_out;
+            const bool live = e < e_end && kk < pk && c < L_prod;
+            vm[u] = 0;
+#pragma unroll
+            for (int t = 0; t < NT; t++) {
+              const unsigned rk = kk - mr[t], rc = c - ml[t];
+              const bool ok = live && ((open_o >> t) & 1u) && rk < c_last && rc < L_src;
+              xv[u][t] = ok ? ld_row(src + (toff[t] + (long long)(int)(rk * L_src + rc))) : 0.0;
+              vm[u] |= (ok ? 1u : 0u) << t;
+            }
+            if (MODE == 1) sl[u] = (e < e_end && kk < sk && c < L_slice) ? sblk[(long long)kk * self_last + (long long)c * slice_cstr] : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < U; u++) {
+            const unsigned e = base + u * 32u + lane;
+            if (e >= e_end) continue;
+            const unsigned kk = __umulhi(e, magic), c = e - kk * L_out;
+            double total_v = 0.0, inner = 0.0;
+            if (finite_sv) {   // branch-free: see the long-row path below
+#pragma unroll
+              for (int t = 0; t < NT; t++) {
+                if (t > 0 && ((gstart >> t) & 1u)) {
+                  total_v = __dadd_rn(total_v, inner);
+                  inner = 0.0;
+                }
+                inner = __dadd_rn(inner, __dmul_rn(xv[u][t], sv[t]));
+              }
+              total_v = __dadd_rn(total_v, inner);
+            } else {
+              bool open = false;
+#pragma unroll
+              for (int t = 0; t < NT; t++) {
+                if ((gstart >> t) & 1u) {
+                  if (open) total_v = __dadd_rn(total_v, inner);
+                  inner = 0.0;
+                  open = ((open_o >> t) & 1u) && (kk - mr[t]) < c_last;
+                }
+                if ((vm[u] >> t) & 1u) inner = __dadd_rn(inner, __dmul_rn(xv[u][t], sv[t]));
+              }
+              if (open) total_v = __dadd_rn(total_v, inner);
+            }
+            const bool a_ok = kk < pk && c < L_prod;
+            const double prod = a_ok ? total_v : 0.0;
+            double rv;
+            if (MODE == 0) rv = prod;
+            else if (MODE == 2) rv = (orow == 0 && e == 0) ? __dadd_rn(prod, slice_base[0]) : prod;
+            else {
+              rv = 0.0;
+              if (a_ok) rv = __dadd_rn(rv, prod);
+              if (kk < sk && c < L_slice) rv = __dadd_rn(rv, sl[u]);
+            }
+            dblk[e] = rv;
+          }
+        }
+      }
+      src = dst;
+      if (step + 1 < p.nsteps) grid_barrier(p.bar, phase);
+      continue;
+    }
     for (unsigned item = gw; item < n_items; item += warps_total) {
       unsigned row, row_end;
       if (G == 1u) {
@@ -654,7 +759,7 @@ __global__ void __launch_bounds__(HD_T, (NT <= 4 ? (MODE == 0 ? 4 : 3) : (NT <= 
 static bool launch_direct_variant(Ctx& ctx, const HornerP& p, int add_mode, const unsigned* final_shape, u64 final_total, const char* tag) {
   if (!ctx.use_direct || p.ne < 2) return false;
   const unsigned L_final = final_shape[p.ne - 1];
-  if (L_final < 48 || final_total < ctx.direct_min) return false;   // short rows: the per-row setup dominates
+  if ((L_final < 48 && p.ne < 3) || final_total < ctx.direct_min) return false;   // short rows need a second row axis to walk blocks
   if (add_mode == 0 && L_final < 192 && !ctx.direct_products_all) return false;   // plain products: the gather kernel wins on shorter rows
   HornerDirectP dp;
   memset(&dp, 0, sizeof(dp));
