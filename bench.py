@@ -567,6 +567,24 @@ def run_ours(args):
         parity["max_rel_err"] = max(parity["max_rel_err"], worst)
         parity["coefficients_checked"] += int(checked)
 
+    if rank == 0 and world > 1 and not args.no_cpu:
+        # N > 1: a small oracle sample of rank 0's own rows of the partitioned e2e result (no CPU baseline here: that is N = 1's)
+        budget = min(args.cpu_budget_gmac, 4.0) * 1e9
+        k1s, _ = cpu_sample_rows(n, d, budget_macs=budget)
+        r, macs, dt = run_cpu_sample(xh_np, yh_np, k1s)
+        got, ref = e2e_out_sample.numpy()[k1s], r[k1s]
+        parity = {"vs": "oracle, same inputs, rows Z[0, k1, ...] and blocks Z[k0 > 0, 0..k1, ...] of rank 0's share of the partitioned e2e result",
+                  "max_rel_err": float(np.max(np.abs(got - ref) / np.abs(ref))), "tolerance": 1e-12,
+                  "coefficients_checked": int(ref.size), "oracle_seconds": dt}
+        local = h_out.numpy()
+        mine = {int(k0): i for i, k0 in enumerate(pp.rows)}
+        blocks = [(k0, k1) for k0, k1 in parity_samples(n, d, budget) if k0 in mine]
+        for k0, k1 in blocks:
+            bref, _ = oracle_block(xh_np, yh_np, k0, k1)
+            parity["max_rel_err"] = max(parity["max_rel_err"], float(np.max(np.abs(local[mine[k0], :k1 + 1] - bref) / np.abs(bref))))
+            parity["coefficients_checked"] += int(bref.size)
+        parity["k0_gt_0_blocks"] = str(blocks)
+
     sweep, sgcl, bounds = None, None, None
     if rank == 0 and world == 1 and not args.no_sweep:
         sweep = run_sweep(ctx, torch, peak, 0.0 if args.no_cpu else args.cpu_budget_gmac * 0.1)
