@@ -441,7 +441,9 @@ __device__ __forceinline__ double ld_row(const double* p) {
   asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
   return v;
 }
-template <int NT, int U, int MODE>
+// GS: terms per group when every group has the same number (1 or 2: the substitution's extent along the last axis), else 0 --
+// with it the group boundaries of the summation are compile-time and the arithmetic carries no selects.
+template <int NT, int U, int MODE, int GS>
 __global__ void __launch_bounds__(HD_T, (NT <= 4 ? (MODE == 0 ? 4 : 3) : (NT <= 8 ? 2 : 1))) k_horner_direct(const __grid_constant__ HornerDirectP dp) {
   const HornerP& p = dp.h;
   const int ne = p.ne;
@@ -570,7 +572,7 @@ __global__ void __launch_bounds__(HD_T, (NT <= 4 ? (MODE == 0 ? 4 : 3) : (NT <= 
             if (finite_sv) {   // branch-free: see the long-row path below
 #pragma unroll
               for (int t = 0; t < NT; t++) {
-                if (t > 0 && ((gstart >> t) & 1u)) {
+                if (t > 0 && (GS ? (t % (GS ? GS : 1)) == 0 : (((gstart >> t) & 1u) != 0u))) {
                   total_v = __dadd_rn(total_v, inner);
                   inner = 0.0;
                 }
@@ -581,7 +583,7 @@ __global__ void __launch_bounds__(HD_T, (NT <= 4 ? (MODE == 0 ? 4 : 3) : (NT <= 
               bool open = false;
 #pragma unroll
               for (int t = 0; t < NT; t++) {
-                if ((gstart >> t) & 1u) {
+                if (GS ? (t % (GS ? GS : 1)) == 0 && t < p.nt : (((gstart >> t) & 1u) != 0u)) {
                   if (open) total_v = __dadd_rn(total_v, inner);
                   inner = 0.0;
                   open = ((open_o >> t) & 1u) && (kk - mr[t]) < c_last;
@@ -695,7 +697,7 @@ __global__ void __launch_bounds__(HD_T, (NT <= 4 ? (MODE == 0 ? 4 : 3) : (NT <= 
               double total_v = 0.0, inner = 0.0;
   #pragma unroll
               for (int t = 0; t < NT; t++) {
-                if (t > 0 && ((gstart >> t) & 1u)) {
+                if (t > 0 && (GS ? (t % (GS ? GS : 1)) == 0 : (((gstart >> t) & 1u) != 0u))) {
                   total_v = __dadd_rn(total_v, inner);
                   inner = 0.0;
                 }
@@ -719,7 +721,7 @@ __global__ void __launch_bounds__(HD_T, (NT <= 4 ? (MODE == 0 ? 4 : 3) : (NT <= 
             bool open = false;
   #pragma unroll
             for (int t = 0; t < NT; t++) {
-              if ((gstart >> t) & 1u) {
+              if (GS ? (t % (GS ? GS : 1)) == 0 && t < p.nt : (((gstart >> t) & 1u) != 0u)) {
                 if (open) total_v = __dadd_rn(total_v, inner);
                 inner = 0.0;
                 open = (openmask >> t) & 1u;
@@ -775,15 +777,34 @@ static bool launch_direct_variant(Ctx& ctx, const HornerP& p, int add_mode, cons
   if (c < 0) return false;
   const void* fn;
   int bucket;
-#define HD_PICK(NT_, U_) (add_mode == 0 ? (const void*)k_horner_direct<NT_, U_, 0> : (add_mode == 1 ? (const void*)k_horner_direct<NT_, U_, 1> : (const void*)k_horner_direct<NT_, U_, 2>))
+  // uniform group size (terms per group): 1 or 2 for the usual substitutions, else 0 = read the group starts at run time
+  int gsz = 0;
+  {
+    int cnt = 0, first = -1;
+    bool uniform = true;
+    for (int t = 0; t <= p.nt; t++) {
+      if (t == p.nt || p.group_start[t]) {
+        if (t > 0) {
+          if (first < 0) first = cnt;
+          uniform = uniform && cnt == first;
+        }
+        cnt = 0;
+      }
+      cnt++;
+    }
+    if (uniform && (first == 1 || first == 2) && p.nt % first == 0) gsz = first;
+  }
+#define HD_PICK3(NT_, U_, GS_) (add_mode == 0 ? (const void*)k_horner_direct<NT_, U_, 0, GS_> : (add_mode == 1 ? (const void*)k_horner_direct<NT_, U_, 1, GS_> : (const void*)k_horner_direct<NT_, U_, 2, GS_>))
+#define HD_PICK(NT_, U_) (gsz == 2 ? HD_PICK3(NT_, U_, 2) : (gsz == 1 ? HD_PICK3(NT_, U_, 1) : HD_PICK3(NT_, U_, 0)))
   if (p.nt <= 2) { fn = HD_PICK(2, 4); bucket = 0; }
   else if (p.nt <= 4) { fn = HD_PICK(4, 2); bucket = 1; }
   else if (p.nt <= 8) { fn = HD_PICK(8, 2); bucket = 2; }
-  else if (p.nt <= 16) { fn = HD_PICK(16, 1); bucket = 3; }
-  else { fn = HD_PICK(32, 1); bucket = 4; }
+  else if (p.nt <= 16) { gsz = 0; fn = HD_PICK3(16, 1, 0); bucket = 3; }
+  else { gsz = 0; fn = HD_PICK3(32, 1, 0); bucket = 4; }
 #undef HD_PICK
-  bucket = bucket * 3 + add_mode;
-  static int per_sm_cached[15][64] = {};
+#undef HD_PICK3
+  bucket = (bucket * 3 + add_mode) * 3 + gsz;
+  static int per_sm_cached[45][64] = {};
   int& per_sm = per_sm_cached[bucket][ctx.device & 63];
   if (per_sm == 0) {
     GTP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, HD_T, 0));
