@@ -623,7 +623,7 @@ __global__ void __launch_bounds__(HD_T, (NT <= 4 ? (MODE == 0 ? 4 : 3) : (NT <= 
       bool in_prod_o = true, in_slice_o = true;
       unsigned open_o = 0, k_last = 0;
       long long so = 0;
-      const double* tp[NT];
+      int tp[NT];   // element offsets into `src` (tensors stay below 2^31 coefficients): one IMAD.WIDE per load, one register per term
       for (; row < row_end; row++) {
         if (need_full) {
           // ---- full decode: outer axes folded into flags / offsets, the last row axis kept as k_last ----
@@ -657,7 +657,7 @@ __global__ void __launch_bounds__(HD_T, (NT <= 4 ? (MODE == 0 ? 4 : 3) : (NT <= 
           so += (long long)k_last * self_last;
 #pragma unroll
           for (int t = 0; t < NT; t++)
-            tp[t] = src + (toff[t] + ((long long)k_last - (long long)p.m[t][al]) * sa_last - (long long)p.m[t][ne - 1] + (long long)c0);
+            tp[t] = (int)(toff[t] + ((long long)k_last - (long long)p.m[t][al]) * sa_last - (long long)p.m[t][ne - 1] + (long long)c0);
           need_full = false;
         }
         // ---- per row: the last row axis ----
@@ -673,7 +673,7 @@ __global__ void __launch_bounds__(HD_T, (NT <= 4 ? (MODE == 0 ? 4 : 3) : (NT <= 
           lo[t] = ml;
           span[t] = (ok && hi > ml) ? hi - ml : 0u;
         }
-        double* drow = dst + ((size_t)row * L_out + c0);
+        const unsigned drow = row * L_out + c0;   // element offset into `dst`
         const double* srow = slice_base + (so + (long long)c0 * slice_cstr);
         const unsigned prod_end = in_prod ? L_prod : 0u, slice_end = (MODE == 1 && in_slice) ? L_slice : 0u;
         // ---- the row: U chunks per trip, every load of all chunks issued before the first use ----
@@ -683,7 +683,7 @@ __global__ void __launch_bounds__(HD_T, (NT <= 4 ? (MODE == 0 ? 4 : 3) : (NT <= 
           for (int u = 0; u < U; u++) {
             const unsigned idx = base + u * W, cu = idx + c0;
   #pragma unroll
-            for (int t = 0; t < NT; t++) xv[u][t] = (cu - lo[t]) < span[t] ? ld_row(tp[t] + idx) : 0.0;
+            for (int t = 0; t < NT; t++) xv[u][t] = (cu - lo[t]) < span[t] ? ld_row(src + (tp[t] + (int)idx)) : 0.0;
             if (MODE == 1) sl[u] = cu < slice_end ? srow[(long long)idx * slice_cstr] : 0.0;
           }
           if (finite_sv) {
@@ -708,7 +708,7 @@ __global__ void __launch_bounds__(HD_T, (NT <= 4 ? (MODE == 0 ? 4 : 3) : (NT <= 
               if (MODE == 0) rv = total_v;
               else if (MODE == 2) rv = (row == 0 && cu == 0) ? __dadd_rn(total_v, slice_base[0]) : total_v;
               else rv = __dadd_rn(__dadd_rn(0.0, total_v), sl[u]);
-              if (cu < L_out) drow[idx] = rv;
+              if (cu < L_out) dst[drow + idx] = rv;
             }
             continue;
           }
@@ -739,7 +739,7 @@ __global__ void __launch_bounds__(HD_T, (NT <= 4 ? (MODE == 0 ? 4 : 3) : (NT <= 
               if (a_ok) rv = __dadd_rn(rv, prod);
               if (cu < slice_end) rv = __dadd_rn(rv, sl[u]);
             }
-            drow[idx] = rv;
+            dst[drow + idx] = rv;
           }
         }
         // ---- advance to the next row of the block ----
@@ -749,7 +749,7 @@ __global__ void __launch_bounds__(HD_T, (NT <= 4 ? (MODE == 0 ? 4 : 3) : (NT <= 
         } else {
           so += self_last;
 #pragma unroll
-          for (int t = 0; t < NT; t++) tp[t] += sa_last;
+          for (int t = 0; t < NT; t++) tp[t] += (int)sa_last;
         }
       }
     }
